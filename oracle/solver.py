@@ -1,0 +1,217 @@
+"""ORACLE: time stepping, Newton loop and Krylov solvers (numpy/scipy restatement).
+
+reference: src/solver/04_Time_Domain.jl:1-80                       (GeneralAlpha, update_OneStep!)
+           src/solver/linear_solver/02_Preconditioner.jl:32-148    (iterative_Solve!, Pr_Jacobi!)
+           src/solver/linear_solver/04_IDRs.jl:1-95                (modify_Omega, idrs!)
+           src/solver/linear_solver/03_BiCGstabl.jl:18-96          (bicgstabl_GS!)
+Random shadow vectors come from a seeded numpy generator (the reference uses unseeded cuRAND),
+so only solver-tolerance agreement of solutions is meaningful (SURVEY.md §7 hard part (f)).
+"""
+import numpy as np
+
+from . import assembly as asm
+
+
+def normalized_norm(x):
+    return np.linalg.norm(x) / np.sqrt(len(x))
+
+
+def update_Time(dom):                                   # :10-18
+    gf = dom.globalfield
+    gf.t += gf.dt
+    L = gf.max_time_level
+    prod_gamma = [float(np.prod(dom.gamma_params[:i])) for i in range(L + 1)]
+    dt_params = [gf.dt ** i for i in range(L + 1)]
+    dom.beta_params = [1.0 / (g * d) for g, d in zip(prod_gamma, dt_params)]
+    dom.K_params = [a * b for a, b in zip(dom.alpha_params[:L + 1], dom.beta_params)]
+
+
+def initialize_dx(dom):                                 # :20-30
+    gf = dom.globalfield
+    n = gf.basicfield_size
+    gf.dx[:] = 0.0
+    for l in range(gf.max_time_level, 0, -1):
+        lo, hi = slice((l - 1) * n, l * n), slice(l * n, (l + 1) * n)
+        gf.dx[lo] = gf.dt * (gf.x[hi] + dom.gamma_params[l - 1] * gf.dx[hi])
+
+
+def update_dx(dom, delta_x):                            # :32-39
+    gf = dom.globalfield
+    n = gf.basicfield_size
+    for l in range(gf.max_time_level + 1):
+        gf.dx[l * n:(l + 1) * n] += dom.beta_params[l] * delta_x
+
+
+def update_x_star(dom):                                 # :41-49
+    gf = dom.globalfield
+    n = gf.basicfield_size
+    gf.x_star[:] = gf.x
+    for l in range(gf.max_time_level + 1):
+        gf.x_star[l * n:(l + 1) * n] += dom.alpha_params[l] * gf.dx[l * n:(l + 1) * n]
+
+
+def update_OneStep(dom, max_iter=4, log=None):          # :59-80
+    gf = dom.globalfield
+    update_Time(dom)
+    initialize_dx(dom)
+    asm.K_linear_func(dom)
+    counter = -1
+    history = []
+    while True:
+        update_x_star(dom)
+        asm.K_nonlinear_func(dom)
+        res = normalized_norm(gf.residue)
+        counter += 1
+        history.append(res)
+        if log:
+            log(f"step {counter} residue = {res}")
+        if res < gf.converge_tol or counter > max_iter:
+            break
+        delta_x = dom.linear_solver(dom)
+        update_dx(dom, -delta_x)
+    gf.x += gf.dx
+    return history
+
+
+# ---------------------------------------------------------------------------------------------
+def Pr_Jacobi(A):
+    """Pr_Jacobi! with Jacobi_By_Diagonal + Mat_Div_Jacobi (02_Preconditioner.jl:103-148); A is scipy CSR, modified in place."""
+    n = A.shape[0]
+    jac = np.ones(n)
+    rows = np.repeat(np.arange(n), np.diff(A.indptr))
+    dmask = A.indices == rows
+    jac[rows[dmask]] = np.abs(A.data[dmask])
+    A.data /= jac[A.indices]
+    return jac
+
+
+def iterative_Solve(dom, Sv_func, max_pass=4, seed=1234, log=None, **kw):
+    """iterative_Solve! (:32-76), right Jacobi only (Pl = Identity)."""
+    gf = dom.globalfield
+    A = asm.csr_from_globalfield(gf).copy()
+    jac = Pr_Jacobi(A)
+    b = gf.residue
+    r = b.copy()
+    x = np.zeros_like(b)
+    rng = np.random.default_rng(seed)
+    pass_number = 1
+    iters = []
+    while True:
+        it = Sv_func(x, A, b, r, tol=gf.converge_tol, rng=rng, **kw)
+        iters.append(it)
+        r[:] = b - A @ x
+        res = normalized_norm(r)
+        if log:
+            log(f"pass {pass_number} with res = {res} iter = {it}.")
+        if res < gf.converge_tol or pass_number >= max_pass:
+            break
+        pass_number += 1
+    dom.last_solve = dict(passes=pass_number, iters=iters, res=res)
+    return x / jac
+
+
+def modify_Omega(v1, v2):                               # 04_IDRs.jl:1-8
+    angle = np.sqrt(2.0) / 2
+    n1, n2 = np.linalg.norm(v1), np.linalg.norm(v2)
+    d = np.dot(v1, v2)
+    rho = abs(d / (n1 * n2))
+    omega = d / (n1 * n1)
+    return omega * angle / rho if rho < angle else omega
+
+
+def idrs(x, A, b, r, tol, maxiter, s=4, rng=None, **kw):    # 04_IDRs.jl:26-95
+    r[:] = b - A @ x
+    if normalized_norm(r) <= tol:
+        return 0
+    it = 1
+    n = len(b)
+    P = [rng.random(n) for _ in range(s)]
+    U = [np.zeros(n) for _ in range(s)]
+    G = [np.zeros(n) for _ in range(s)]
+    M = np.eye(s)
+    f = np.zeros(s)
+    omega = 1.0
+    while True:
+        for i in range(s):
+            f[i] = np.dot(P[i], r)
+        for k in range(s):
+            c = np.linalg.solve(np.tril(M[k:, k:]), f[k:])
+            V = c[0] * G[k]
+            Q = c[0] * U[k]
+            for i in range(k + 1, s):
+                V += c[i - k] * G[i]
+                Q += c[i - k] * U[i]
+            V = r - V
+            U[k] = Q + omega * V
+            G[k] = A @ U[k]
+            for i in range(k):
+                alpha = np.dot(P[i], G[k]) / M[i, i]
+                G[k] -= alpha * G[i]
+                U[k] -= alpha * U[i]
+            for i in range(k, s):
+                M[i, k] = np.dot(P[i], G[k])
+            beta = f[k] / M[k, k]
+            x += beta * U[k]
+            r -= beta * G[k]
+            if normalized_norm(r) <= tol or it >= maxiter:
+                return it
+            f[k + 1:] -= beta * M[k + 1:, k]
+            it += 1
+        Ar = A @ r
+        omega = modify_Omega(Ar, r)
+        x += omega * r
+        r -= omega * Ar
+        if normalized_norm(r) <= tol or it >= maxiter:
+            return it
+        it += 1
+
+
+def bicgstabl_GS(x, A, b, r, tol, maxiter, s=2, rng=None, **kw):   # 03_BiCGstabl.jl:18-96
+    r[:] = b - A @ x
+    if normalized_norm(r) <= tol:
+        return 0
+    it = 1
+    n = len(b)
+    gam, gamp, gampp, sig = np.zeros(s), np.zeros(s), np.zeros(s), np.zeros(s)
+    tau = np.zeros((s, s))
+    omega = rho0 = 1.0
+    alpha = 0.0
+    r_shadow = rng.random(n)
+    R = [r] + [np.zeros(n) for _ in range(s)]       # R[1] aliases r (:40)
+    U = [np.zeros(n) for _ in range(s + 1)]
+    while True:
+        rho0 *= -omega
+        for j in range(s):
+            rho1 = np.dot(r_shadow, R[j])
+            beta = alpha * rho1 / rho0
+            rho0 = rho1
+            for i in range(j + 1):
+                U[i][:] = R[i] - beta * U[i]
+            U[j + 1][:] = A @ U[j]
+            alpha = rho0 / np.dot(r_shadow, U[j + 1])
+            for i in range(j + 1):
+                R[i] -= alpha * U[i + 1]
+            R[j + 1][:] = A @ R[j]
+            x += alpha * U[0]
+        for j in range(s):
+            for i in range(j):
+                tau[i, j] = np.dot(R[i + 1], R[j + 1]) / sig[i]
+                R[j + 1] -= tau[i, j] * R[i + 1]
+            sig[j] = np.dot(R[j + 1], R[j + 1])
+            gamp[j] = np.dot(R[0], R[j + 1]) / sig[j]
+        gam[s - 1] = gamp[s - 1]
+        omega = gam[s - 1]
+        for j in range(s - 2, -1, -1):
+            gam[j] = gamp[j] - np.dot(tau[j, j + 1:s], gam[j + 1:s])
+        for j in range(s - 1):
+            gampp[j] = gam[j + 1] + np.dot(tau[j, j + 1:s - 1], gam[j + 2:s])
+        x += gam[0] * R[0]
+        R[0] -= gamp[s - 1] * R[s]
+        U[0] -= gam[s - 1] * U[s]
+        for j in range(s - 1):
+            U[0] -= gam[j] * U[j + 1]
+            x += gampp[j] * R[j + 1]
+            R[0] -= gamp[j] * R[j + 1]
+        it += s
+        if normalized_norm(R[0]) <= tol or it >= maxiter:
+            return it
