@@ -1,0 +1,179 @@
+/* metafem_b200.h -- C ABI of libmetafem_b200.so
+ *
+ * B200-native (sm_100a) replacement for MetaFEM.jl's hot path: element evaluation ->
+ * scatter-assembly into CSR -> Jacobi-preconditioned Krylov solve. These entry points are what
+ * the Julia side binds with `ccall`; every test and benchmark in this
+ * repository drives exactly the same symbols through Python ctypes.
+ *
+ * Conventions (reference: FEM_Int = Int32, FEM_Float = Float64, src/misc/02_Global_Macros.jl:123-124):
+ *  - all index arrays are 1-based int32, all tables column-major (first index fastest), exactly
+ *    as the reference stores them;
+ *  - every array argument may be a device pointer, a CUDA unified pointer (the reference's
+ *    default array type, src/misc/04_GPU_Utils.jl:8) or a plain/pinned host pointer; host
+ *    buffers are staged through the context's stream inside the call;
+ *  - the library borrows caller memory only for the duration of a call;
+ *  - every function returns MFB_OK (0) or a negative error code; mfb_last_error() gives text.
+ *    MFB_NOT_CONVERGED (1) is a warning: results are valid, the reference only prints in that
+ *    case (src/solver/linear_solver/02_Preconditioner.jl:66-68).
+ */
+#ifndef METAFEM_B200_H
+#define METAFEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mfb_ctx mfb_ctx;
+
+enum {
+    MFB_OK = 0,
+    MFB_NOT_CONVERGED = 1,
+    MFB_ERR_CUDA = -1,
+    MFB_ERR_NVRTC = -2,
+    MFB_ERR_ARG = -3,
+    MFB_ERR_STATE = -4,
+    MFB_ERR_NCCL = -5
+};
+
+/* Krylov methods: Sv_func! of iterative_Solve! (02_Preconditioner.jl:32) */
+enum { MFB_IDRS = 0 /* idrs!, 04_IDRs.jl:26-95 */, MFB_BICGSTABL_GS = 1 /* bicgstabl_GS!, 03_BiCGstabl.jl:18-96 */ };
+
+/* vectors of GlobalField (src/solver/01_Types.jl:110-132) */
+enum { MFB_VEC_X = 0, MFB_VEC_DX = 1, MFB_VEC_X_STAR = 2, MFB_VEC_RESIDUE = 3 };
+/* matrices of GlobalField */
+enum { MFB_MAT_K_LINEAR = 0, MFB_MAT_K_TOTAL = 1 };
+
+/* ---- context ------------------------------------------------------------------------- */
+int mfb_create(mfb_ctx **ctx, int device);
+int mfb_destroy(mfb_ctx *ctx);
+const char *mfb_last_error(mfb_ctx *ctx);
+/* use a caller stream (cudaStream_t); NULL = the context's own stream */
+int mfb_set_stream(mfb_ctx *ctx, void *cuda_stream);
+/* number of kernels this library has launched on ctx since creation (bench.py "gpu_launches") */
+int64_t mfb_launch_count(mfb_ctx *ctx);
+int mfb_synchronize(mfb_ctx *ctx);
+
+/* ---- mesh tables ---------------------------------------------------------------------
+ * Replaces the element tables produced by mesh_Classical + update_Mesh
+ * (src/mesh/unstructured_mesh/2_Interface.jl:7-39,98-108; 4_Update_Integrator.jl:2-33):
+ * the library takes the connectivity, node coordinates and REFERENCE-element tables and
+ * evaluates Jacobians / physical gradients / w*detJ on the fly inside the element kernels, so
+ * the 34.6 kB/element integral_vals table is never materialised.
+ *   controlpoint_IDs [n_a, n_el]  elements.controlpoint_IDs (== global_cpIDs for one workpiece)
+ *   x1,x2,x3         [N]          controlpoints.x1/x2/x3
+ *   ref_itp_vals     [n_q, n_a, 2, 2, 2]  Classical_Discretization.ref_itp_vals (max_sd_order = 1)
+ *   itg_weight       [n_q]
+ */
+int mfb_mesh_set(mfb_ctx *ctx, int n_a, int64_t n_el, int64_t N, int n_q,
+                 const int32_t *controlpoint_IDs, const double *x1, const double *x2, const double *x3,
+                 const double *ref_itp_vals, const double *itg_weight);
+
+/* Boundary tables (4_Update_Integrator.jl:35-75; 3_InitializeMesh.jl:119-130,165-178):
+ *   bdy_ref_itp_vals       [n_qb, n_a, 2, 2, 2, n_faces]   one table per local face (eindex)
+ *   bdy_itg_weights        [n_qb, n_faces]
+ *   bdy_tangent_directions [n_qb, 3, 2, n_faces]
+ *   facet_element_ID / facet_element_eindex [n_facets]     facets.element_ID / element_eindex
+ */
+int mfb_facets_set(mfb_ctx *ctx, int n_faces, int n_qb, const double *bdy_ref_itp_vals,
+                   const double *bdy_itg_weights, const double *bdy_tangent_directions,
+                   int64_t n_facets, const int32_t *facet_element_ID, const int32_t *facet_element_eindex);
+/* bg_fIDs[bg_ID] (1_Types.jl:61): facet IDs (1-based) of one boundary group */
+int mfb_boundary_group_set(mfb_ctx *ctx, int bg_ID, int64_t n, const int32_t *facet_IDs);
+
+/* ---- DOF numbering + sparsity pattern ---------------------------------------------------
+ * Replaces assemble_Global_Variables! / assemble_SparseID! (src/solver/03_GlobalAssembly.jl:6-37,77-168)
+ * and sort_CUSPARSE_COO!/generate_J_ptr (src/misc/04_GPU_Utils.jl:87-118).
+ *   n_var          number of basic variables (length(basic_vars))
+ *   max_time_level highest time-derivative order (x holds (max_time_level+1)*n_var*N values)
+ *   sparse_mapping [2, n_blocks] (dual_pos, base_pos) of block m, 0-based, in block order
+ * Outputs: nnz = n_blocks*sparse_unitsize, sparse_unitsize = number of distinct (node,node) pairs.
+ * The pattern is kept on the device in CSR order; sparse IDs are DEFINED as CSR positions
+ * (the reference's hash-slot order is an internal permutation), so
+ * K_val_ids is the identity.
+ */
+int mfb_pattern_build(mfb_ctx *ctx, int n_var, int max_time_level, int n_blocks,
+                      const int32_t *sparse_mapping, int64_t *nnz, int64_t *sparse_unitsize);
+/* Reference-layout copies for parity: K_I, K_J [nnz] (sorted by row then column, 1-based),
+ * K_J_ptr [n+1] (1-based), K_val_ids [nnz], sparse_IDs_by_el [n_a, n_a, n_el] (CSR position of
+ * block 0, 1-based; add m*... via mfb_block_entry_shift). Any pointer may be NULL. */
+int mfb_pattern_get(mfb_ctx *ctx, int32_t *K_I, int32_t *K_J, int32_t *K_J_ptr, int32_t *K_val_ids);
+
+/* ---- fields ------------------------------------------------------------------------------
+ * CONTROLPOINT_VAR external fields (controlpoints.<sym>, 05_CodeGenerator.jl:28-35), by local symbol. */
+int mfb_field_set(mfb_ctx *ctx, const char *local_sym, const double *values /* [N] */);
+/* GLOBAL_VAR scalars (physics.global_vars[:sym], read at call time, 05_CodeGenerator.jl:21-27) */
+int mfb_global_set(mfb_ctx *ctx, const char *sym, double value);
+/* GlobalField vectors; n = (max_time_level+1)*n_var*N for x/dx/x_star, n_var*N for residue.
+ * Reference layout: index = g + v*N + l*n  (03_GlobalAssembly.jl:52). */
+int mfb_vector_set(mfb_ctx *ctx, int which, const double *values, int64_t n);
+int mfb_vector_get(mfb_ctx *ctx, int which, double *values, int64_t n);
+/* CSR values (K_linear / K_total) in reference CSR order: K[K_val_ids] of the reference */
+int mfb_matrix_get(mfb_ctx *ctx, int which, double *values, int64_t nnz);
+
+/* ---- generated element kernels ----------------------------------------------------------
+ * Replaces compile_Updater_GPU (src/solver/05_CodeGenerator.jl:265-291). `cuda_src` is the CUDA C
+ * emitted by the front end's term emitter (sibling of parse_Term2Expr!, src/symbolics/08_Tensor.jl:214-233)
+ * on top of the library's assembly skeleton ("mfb_skeleton.cuh", resolvable as an #include);
+ * it is compiled with NVRTC for sm_100a. One descriptor per generated block
+ * (domain first, then boundary groups, as gen_CodeBody orders them, :156-196). */
+typedef struct {
+    int32_t kind;                 /* 0 = domain elements, 1 = boundary group */
+    int32_t bg_ID;                /* boundary group ID when kind == 1 */
+    const char *linear_kernel;    /* entry point writing K_linear, or NULL */
+    const char *nonlinear_kernel; /* entry point writing residue (+ K_total), or NULL */
+    int32_t n_cp_vars;            /* CONTROLPOINT_VAR fields the kernels read, in argument order */
+    const char *const *cp_var_names;
+    int32_t n_globals;            /* GLOBAL_VAR scalars, in argument order */
+    const char *const *global_names;
+    int32_t threads_per_block;    /* launch shape chosen by the emitter */
+    int32_t smem_bytes;           /* dynamic shared memory per block */
+    int32_t has_nonlinear_K;      /* 1 if the nonlinear kernel adds K terms */
+} mfb_block_desc;
+int mfb_kernel_compile(mfb_ctx *ctx, const char *cuda_src, int n_blocks, const mfb_block_desc *blocks);
+/* Compile-only check of an emitted translation unit (needs no device): writes the NVRTC log (or the
+ * error text) to log_out and, if cubin_path is not NULL, the sm_100a cubin to that file. */
+int mfb_kernel_check(const char *cuda_src, const char *cubin_path, char *log_out, int log_len);
+/* NVRTC log of the last compilation (valid until the next compile) */
+const char *mfb_compile_log(mfb_ctx *ctx);
+
+/* K_linear_func: K_linear .= 0, then every linear gradient term (05_CodeGenerator.jl:265-276) */
+int mfb_assemble_linear(mfb_ctx *ctx, const double *K_params, int n_params);
+/* K_nonlinear_func: residue .= 0; K_total .= K_linear; residual + nonlinear gradient terms,
+ * evaluated at the context's x_star (05_CodeGenerator.jl:278-288). t and dt are the GLOBAL_VARs :t/:dt. */
+int mfb_assemble_nonlinear(mfb_ctx *ctx, const double *K_params, int n_params, double t, double dt);
+
+/* ---- linear algebra ---------------------------------------------------------------------
+ * y = K * x in reference numbering (mul!, src/misc/04_GPU_Utils.jl:131). */
+int mfb_spmv(mfb_ctx *ctx, int which_matrix, const double *x, double *y, int64_t n);
+
+typedef struct {
+    int32_t passes;        /* restart passes used */
+    int32_t iterations;    /* Krylov iterations summed over passes */
+    int32_t spmv_count;    /* SpMV launches */
+    int32_t converged;     /* 1 if res < tol */
+    double residual;       /* final true residual ||b - A x||_2 / sqrt(n) */
+    double initial_residual;
+} mfb_solve_info;
+/* iterative_Solve!(globalfield; Sv_func!, Pr_func! = Pr_Jacobi!, max_pass, maxiter, s)
+ * (02_Preconditioner.jl:32-76): solves K_total * delta = residue with right-Jacobi scaling,
+ * absolute tolerance on ||r||/sqrt(n); writes delta (reference numbering) to delta_out [n]
+ * (may be NULL: result stays in the context for mfb_update_dx). */
+int mfb_krylov_solve(mfb_ctx *ctx, int method, int s, int maxiter, int max_pass, double tol,
+                     uint64_t seed, double *delta_out, mfb_solve_info *info);
+
+/* ---- time stepping (src/solver/04_Time_Domain.jl) ----------------------------------------
+ * Device-resident versions of initialize_dx! (:20-30), update_x_star! (:41-49),
+ * update_dx! with the last solve's delta (:32-39, called with -delta as update_OneStep! does, :77),
+ * x .+= dx (:79) and normalized_norm(residue) (:51,69). */
+int mfb_initialize_dx(mfb_ctx *ctx, double dt, const double *gamma_params, int n_gamma);
+int mfb_update_x_star(mfb_ctx *ctx, const double *alpha_params, int n_alpha);
+int mfb_update_dx(mfb_ctx *ctx, const double *beta_params, int n_beta, double sign);
+int mfb_commit_step(mfb_ctx *ctx);
+int mfb_residue_norm(mfb_ctx *ctx, double *normalized_norm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METAFEM_B200_H */

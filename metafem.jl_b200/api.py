@@ -1,0 +1,284 @@
+"""Host-side mirror of MetaFEM's interface for the hot path (same names, same argument meaning).
+
+In production these bodies are the Julia overrides shown in INTEGRATION.md; Julia is absent in
+this environment, so the identical call sequence is issued from Python through the C ABI.
+
+  FEM_Domain / GlobalField / GeneralAlpha      reference src/solver/01_Types.jl:110-168, 04_Time_Domain.jl:1-8
+  assemble_Global_Variables / assemble_X / dessemble_X       src/solver/03_GlobalAssembly.jl:6-75
+  compile_Updater_GPU                                        src/solver/05_CodeGenerator.jl:265-291
+  update_OneStep                                             src/solver/04_Time_Domain.jl:59-80
+  iterative_Solve (Sv_func = "idrs" | "bicgstabl_GS")        src/solver/linear_solver/02_Preconditioner.jl:32-76
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import emitter
+from . import lib as L
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class GeneralAlpha:
+    """04_Time_Domain.jl:1-8."""
+
+    def __init__(self, dissipative=False):
+        self.alpha_params = (1.0, 1.0, 1.0)
+        self.gamma_params = (1.0, 1.0) if dissipative else (0.5, 0.5)
+        self.beta_params = []
+        self.K_params = []
+
+
+class GlobalField:
+    """Scalars of GlobalField (01_Types.jl:110-132); the arrays live on the device behind the context."""
+
+    def __init__(self):
+        self.max_time_level = 0
+        self.basicfield_size = 0
+        self.converge_tol = 0.0
+        self.t = 0.0
+        self.dt = 1.0
+        self.nnz = 0
+        self.sparse_unitsize = 0
+
+
+class MeshTables:
+    """The arrays the front end (mesh_Classical + Classical_Discretization) hands to the hot path.
+
+    All in the reference's layout: 1-based int32 IDs, column-major tables (numpy arrays are passed
+    Fortran-ordered).
+      controlpoint_IDs (n_a, n_el); x (3, N); ref_itp_vals (n_q, n_a, 2,2,2); itg_weight (n_q,)
+      bdy_ref_itp_vals (n_qb, n_a, 2,2,2, n_faces); bdy_itg_weights (n_qb, n_faces);
+      bdy_tangent_directions (n_qb, 3, 2, n_faces); facet_element_ID, facet_element_eindex (n_facets,)
+      bg_fIDs {bg_ID: facet IDs}
+    """
+
+    def __init__(self, controlpoint_IDs, x, ref_itp_vals, itg_weight, bdy_ref_itp_vals=None, bdy_itg_weights=None,
+                 bdy_tangent_directions=None, facet_element_ID=None, facet_element_eindex=None, bg_fIDs=None):
+        self.controlpoint_IDs = np.asfortranarray(controlpoint_IDs, dtype=np.int32)
+        self.x = _f64(x)
+        self.ref_itp_vals = np.asfortranarray(ref_itp_vals, dtype=np.float64)
+        self.itg_weight = _f64(itg_weight)
+        self.bdy_ref_itp_vals = None if bdy_ref_itp_vals is None else np.asfortranarray(bdy_ref_itp_vals, dtype=np.float64)
+        self.bdy_itg_weights = None if bdy_itg_weights is None else np.asfortranarray(bdy_itg_weights, dtype=np.float64)
+        self.bdy_tangent_directions = None if bdy_tangent_directions is None else np.asfortranarray(
+            bdy_tangent_directions, dtype=np.float64)
+        self.facet_element_ID = None if facet_element_ID is None else _i32(facet_element_ID)
+        self.facet_element_eindex = None if facet_element_eindex is None else _i32(facet_element_eindex)
+        self.bg_fIDs = dict(bg_fIDs or {})
+
+    @property
+    def variable_size(self):
+        return self.x.shape[1]
+
+
+class FEM_Domain:
+    """One-workpiece FEM_Domain (01_Types.jl:147-168): mesh tables + kernel spec + device context."""
+
+    def __init__(self, tables, spec, dim=3, dissipative=True, device=0):
+        self.dim = dim
+        self.tables = tables
+        self.spec = spec
+        self.time_discretization = GeneralAlpha(dissipative=dissipative)
+        self.globalfield = GlobalField()
+        self.global_vars = {}
+        self.K_linear_func = None
+        self.K_nonlinear_func = None
+        self.linear_solver = None
+        self.last_solve = None
+        N = tables.variable_size
+        # controlpoints.<sym> tables (host copies, like cpts.T / cpts.d1 in the example scripts)
+        self.controlpoints = {}
+        for b in spec["basic_vars"]:
+            for td in range(spec["max_time_level"] + 1):
+                self.controlpoints[b + (f"_t{td}" if td else "")] = np.zeros(N)
+        for v in spec["cp_vars"]:
+            self.controlpoints[v] = np.zeros(N)
+        self.ctx = L.Context(device)
+        t = tables
+        n_a, n_el = t.controlpoint_IDs.shape
+        self.ctx.call("mfb_mesh_set", n_a, n_el, N, t.ref_itp_vals.shape[0], L.ptr(t.controlpoint_IDs),
+                      L.ptr(_f64(t.x[0])), L.ptr(_f64(t.x[1])), L.ptr(_f64(t.x[2])), L.ptr(t.ref_itp_vals),
+                      L.ptr(t.itg_weight))
+        if t.bdy_ref_itp_vals is not None and t.facet_element_ID is not None:
+            self.ctx.call("mfb_facets_set", t.bdy_ref_itp_vals.shape[-1], t.bdy_ref_itp_vals.shape[0],
+                          L.ptr(t.bdy_ref_itp_vals), L.ptr(t.bdy_itg_weights), L.ptr(t.bdy_tangent_directions),
+                          len(t.facet_element_ID), L.ptr(t.facet_element_ID), L.ptr(t.facet_element_eindex))
+            for bg, ids in t.bg_fIDs.items():
+                ids = _i32(ids)
+                self.ctx.call("mfb_boundary_group_set", int(bg), len(ids), L.ptr(ids))
+
+    # -- vectors / matrices in reference layout ------------------------------------------------
+    def get_vector(self, which):
+        gf = self.globalfield
+        n = gf.basicfield_size * (1 if which == L.VEC_RESIDUE else gf.max_time_level + 1)
+        out = np.empty(n)
+        self.ctx.call("mfb_vector_get", which, L.ptr(out), n)
+        return out
+
+    def set_vector(self, which, v):
+        v = _f64(v)
+        self.ctx.call("mfb_vector_set", which, L.ptr(v), len(v))
+
+    def get_matrix(self, which=L.MAT_K_TOTAL):
+        out = np.empty(self.globalfield.nnz)
+        self.ctx.call("mfb_matrix_get", which, L.ptr(out), len(out))
+        return out
+
+    def get_pattern(self):
+        gf = self.globalfield
+        K_I, K_J = np.empty(gf.nnz, np.int32), np.empty(gf.nnz, np.int32)
+        K_J_ptr, K_val_ids = np.empty(gf.basicfield_size + 1, np.int32), np.empty(gf.nnz, np.int32)
+        self.ctx.call("mfb_pattern_get", L.ptr(K_I), L.ptr(K_J), L.ptr(K_J_ptr), L.ptr(K_val_ids))
+        return K_I, K_J, K_J_ptr, K_val_ids
+
+    def sync_fields(self):
+        """Push controlpoints.<CONTROLPOINT_VAR> and physics.global_vars to the device (read at call time in the reference)."""
+        for v in self.spec["cp_vars"]:
+            self.ctx.call("mfb_field_set", v.encode(), L.ptr(_f64(self.controlpoints[v])))
+        for g in self.spec["globals"]:
+            self.ctx.call("mfb_global_set", g.encode(), float(self.global_vars[g]))
+
+    def close(self):
+        self.ctx.close()
+
+
+def _x_slices(dom):
+    spec, gf, N = dom.spec, dom.globalfield, dom.tables.variable_size
+    for pos, b in enumerate(spec["basic_vars"]):
+        for td in range(spec["max_time_level"] + 1):
+            s = pos * N + td * gf.basicfield_size
+            yield b + (f"_t{td}" if td else ""), slice(s, s + N)
+
+
+def assemble_Global_Variables(fem_domain):
+    """assemble_Global_Variables! (03_GlobalAssembly.jl:6-37): DOF numbering, x/dx/x_star/residue, sparsity pattern."""
+    dom, spec, gf = fem_domain, fem_domain.spec, fem_domain.globalfield
+    N = dom.tables.variable_size
+    gf.basicfield_size = len(spec["basic_vars"]) * N
+    gf.max_time_level = spec["max_time_level"]
+    mapping = _i32(np.array(spec["sparse_mapping"], dtype=np.int32).reshape(-1, 2))
+    nnz, unit = C.c_int64(0), C.c_int64(0)
+    dom.ctx.call("mfb_pattern_build", len(spec["basic_vars"]), gf.max_time_level, len(mapping), L.ptr(mapping),
+                 C.byref(nnz), C.byref(unit))
+    gf.nnz, gf.sparse_unitsize = nnz.value, unit.value
+    assemble_X(dom)
+
+
+def assemble_X(fem_domain):
+    """assemble_X! (:44-56): controlpoints.<var> -> x."""
+    gf = fem_domain.globalfield
+    x = np.zeros((gf.max_time_level + 1) * gf.basicfield_size)
+    for sym, sl in _x_slices(fem_domain):
+        x[sl] = fem_domain.controlpoints[sym]
+    fem_domain.set_vector(L.VEC_X, x)
+
+
+def dessemble_X(fem_domain):
+    """dessemble_X! (:63-75): x -> controlpoints.<var>."""
+    x = fem_domain.get_vector(L.VEC_X)
+    for sym, sl in _x_slices(fem_domain):
+        fem_domain.controlpoints[sym][:] = x[sl]
+
+
+def compile_Updater_GPU(domain_ID, fem_domain, tpb=128):
+    """compile_Updater_GPU (05_CodeGenerator.jl:265-291): emit CUDA C for every block, compile with NVRTC,
+    install K_linear_func / K_nonlinear_func. Returns the generated source (the reference returns the Exprs)."""
+    dom, t = fem_domain, fem_domain.tables
+    n_a, n_q = t.controlpoint_IDs.shape[0], t.ref_itp_vals.shape[0]
+    n_qb = t.bdy_ref_itp_vals.shape[0] if t.bdy_ref_itp_vals is not None else 0
+    src, descs = emitter.emit(dom.spec, n_a, n_q, n_qb, tpb=tpb)
+    arr = (L.BlockDesc * len(descs))()
+    keep = []
+    for i, d in enumerate(descs):
+        cps = (C.c_char_p * max(len(d["cp_var_names"]), 1))(*[s.encode() for s in d["cp_var_names"]])
+        gls = (C.c_char_p * max(len(d["global_names"]), 1))(*[s.encode() for s in d["global_names"]])
+        keep += [cps, gls]
+        arr[i].kind, arr[i].bg_ID = d["kind"], d["bg_ID"]
+        arr[i].linear_kernel = d["linear_kernel"].encode() if d["linear_kernel"] else None
+        arr[i].nonlinear_kernel = d["nonlinear_kernel"].encode() if d["nonlinear_kernel"] else None
+        arr[i].n_cp_vars, arr[i].cp_var_names = len(d["cp_var_names"]), cps
+        arr[i].n_globals, arr[i].global_names = len(d["global_names"]), gls
+        arr[i].threads_per_block, arr[i].smem_bytes = d["threads_per_block"], d["smem_bytes"]
+        arr[i].has_nonlinear_K = d["has_nonlinear_K"]
+    dom.ctx.call("mfb_kernel_compile", src.encode(), len(descs), arr)
+
+    def update_K_Linear(time_discretization, fem_domain=dom):
+        kp = _f64(time_discretization.K_params)
+        fem_domain.sync_fields()
+        fem_domain.ctx.call("mfb_assemble_linear", L.ptr(kp), len(kp))
+
+    def update_K_NonLinear(time_discretization, fem_domain=dom):
+        kp = _f64(time_discretization.K_params)
+        gf = fem_domain.globalfield
+        fem_domain.sync_fields()
+        fem_domain.ctx.call("mfb_assemble_nonlinear", L.ptr(kp), len(kp), gf.t, gf.dt)
+
+    dom.K_linear_func, dom.K_nonlinear_func = update_K_Linear, update_K_NonLinear
+    dom.generated_source = src
+    return src
+
+
+def update_Time(globalfield, td):
+    """update_Time! (04_Time_Domain.jl:10-18)."""
+    globalfield.t += globalfield.dt
+    Lv = globalfield.max_time_level
+    prod_gamma = [float(np.prod(td.gamma_params[:i])) for i in range(Lv + 1)]
+    dt_params = [globalfield.dt ** i for i in range(Lv + 1)]
+    td.beta_params = [1.0 / (g * d) for g, d in zip(prod_gamma, dt_params)]
+    td.K_params = [a * b for a, b in zip(td.alpha_params[:Lv + 1], td.beta_params)]
+
+
+def update_OneStep(time_discretization, max_iter=4, fem_domain=None, log=None):
+    """update_OneStep! (04_Time_Domain.jl:59-80); vectors stay on the device."""
+    dom, gf, td = fem_domain, fem_domain.globalfield, time_discretization
+    update_Time(gf, td)
+    gam = _f64(td.gamma_params)
+    dom.ctx.call("mfb_initialize_dx", gf.dt, L.ptr(gam), len(gam))
+    dom.K_linear_func(td, fem_domain=dom)
+    alpha, beta = _f64(td.alpha_params), _f64(td.beta_params)
+    counter = -1
+    history = []
+    while True:
+        dom.ctx.call("mfb_update_x_star", L.ptr(alpha), len(alpha))
+        dom.K_nonlinear_func(td, fem_domain=dom)
+        res = C.c_double(0.0)
+        dom.ctx.call("mfb_residue_norm", C.byref(res))
+        counter += 1
+        history.append(res.value)
+        if log:
+            log(f"step {counter} residue = {res.value}")
+        if res.value < gf.converge_tol or counter > max_iter:
+            break
+        dom.linear_solver(dom)
+        dom.ctx.call("mfb_update_dx", L.ptr(beta), len(beta), -1.0)      # update_dx!(globalfield, .- delta_x, ...)
+    dom.ctx.call("mfb_commit_step")
+    return history
+
+
+_METHODS = {"idrs": L.MFB_IDRS, "idrs!": L.MFB_IDRS, "bicgstabl_GS": L.MFB_BICGSTABL_GS, "bicgstabl_GS!": L.MFB_BICGSTABL_GS}
+
+
+def iterative_Solve(fem_domain, Sv_func="idrs", max_pass=4, maxiter=2000, s=4, seed=1234, want_delta=False, log=None):
+    """iterative_Solve!(globalfield; Sv_func!, max_pass, maxiter, s) (02_Preconditioner.jl:32-76), right-Jacobi."""
+    if Sv_func not in _METHODS:
+        raise ValueError(f"Sv_func {Sv_func!r} is not on the B200 hot path (supported: idrs, bicgstabl_GS)")
+    dom, gf = fem_domain, fem_domain.globalfield
+    info = L.SolveInfo()
+    delta = np.empty(gf.basicfield_size) if want_delta else None
+    rc = dom.ctx.call("mfb_krylov_solve", _METHODS[Sv_func], int(s), int(maxiter), int(max_pass),
+                      float(gf.converge_tol), int(seed), L.ptr(delta), C.byref(info))
+    dom.last_solve = dict(passes=info.passes, iterations=info.iterations, spmv=info.spmv_count,
+                          converged=bool(info.converged), residual=info.residual,
+                          initial_residual=info.initial_residual)
+    if log:
+        log(f"solver {Sv_func}: initial res = {info.initial_residual}, passes = {info.passes}, "
+            f"iter = {info.iterations}, res = {info.residual}" + ("" if rc == 0 else "  (not converged)"))
+    return delta

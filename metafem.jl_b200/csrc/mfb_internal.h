@@ -1,0 +1,138 @@
+// mfb_internal.h -- context and helpers shared by the translation units of libmetafem_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/metafem_b200.h"
+#include "mfb_skeleton.cuh"
+
+#define MFB_CUDA(call)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (call);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                       ":" + std::to_string(__LINE__) + ")";                                \
+            return MFB_ERR_CUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+
+#define MFB_REQUIRE(cond, code, msg)  \
+    do {                              \
+        if (!(cond)) {                \
+            ctx->err = (msg);         \
+            return (code);            \
+        }                             \
+    } while (0)
+
+#define MFB_TRY(expr)                 \
+    do {                              \
+        int _s = (expr);              \
+        if (_s < 0) return _s;        \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        if (count == n && p) return cudaSuccess;
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+struct BlockKernels {
+    int kind = 0, bg_ID = 0;
+    cudaKernel_t lin = nullptr, nonlin = nullptr;
+    std::vector<std::string> cp_vars, globals;
+    int tpb = 128, smem = 0, has_nonlinear_K = 0;
+};
+
+struct BoundaryGroup {
+    DevBuf<int> elem, face;  // 0-based host element and local face of each facet of the group
+    int64_t n = 0;
+};
+
+struct Comm;  // mfb_dist.cu
+
+struct mfb_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err, compile_log;
+    int64_t launches = 0;
+    int sm_count = 148;
+
+    // ---- mesh ----
+    int n_a = 0, n_q = 0, n_faces = 0, n_qb = 0;
+    int64_t n_el = 0, N = 0, n_facets = 0;
+    DevBuf<int> conn_ref;     // [n_el][n_a] 0-based reference node ids
+    DevBuf<int> conn;         // [n_el][n_a] internal node ids
+    DevBuf<double> xyz;       // [N][3] internal order
+    DevBuf<double> ref, wq;   // domain tables [4][n_q][n_a], [n_q]
+    DevBuf<double> bref, bwq, btan;  // boundary tables per face
+    DevBuf<int> facet_elem, facet_face;  // [n_facets] 0-based
+    std::map<int, BoundaryGroup> groups;
+
+    // ---- numbering / pattern ----
+    int n_var = 0, L1 = 1, n_blocks = 0;
+    std::vector<int> sparse_mapping;  // [n_blocks][2]
+    std::vector<int> block_of;        // [n_var*n_var] -> block number or -1
+    DevBuf<int> perm;       // perm[ref node] = internal node
+    DevBuf<int> iperm;      // iperm[internal] = ref node
+    DevBuf<int> nodeptr;    // [N+1] node graph CSR (internal)
+    DevBuf<int> nodecol;    // [U]
+    DevBuf<int> emap;       // [n_el][n_a*n_a]
+    int64_t U = 0;          // sparse_unitsize
+    DevBuf<int> ref_pos;    // [U] position of entry inside its row, ranked by reference column id (lazy)
+
+    // ---- state (internal layout) ----
+    DevBuf<double> x, dx, x_star;  // [L1][N][n_var]
+    DevBuf<double> residue;        // [N][n_var]
+    DevBuf<double> K_linear, K_total;  // [U][n_var*n_var]
+    DevBuf<double> delta;          // last solve result [N][n_var]
+    bool have_delta = false;
+    std::map<std::string, DevBuf<double>> fields;  // internal order [N]
+    std::map<std::string, double> globals;
+
+    // ---- kernels ----
+    cudaLibrary_t lib = nullptr;
+    std::vector<BlockKernels> blocks;
+    bool any_nonlinear_K = false;
+
+    // ---- krylov workspace ----
+    std::vector<DevBuf<double>> work;
+    DevBuf<double> jac, scal;   // Jacobi vector, device scalars
+    double* h_scal = nullptr;   // pinned host mirror of scal
+
+    // ---- staging ----
+    DevBuf<unsigned char> stage;
+
+    Comm* comm = nullptr;
+};
+
+// staging: returns a device-readable pointer for `src` (device/unified/pinned pass through; pageable host is copied)
+int mfb_stage_in(mfb_ctx* ctx, const void* src, size_t bytes, void* dev_dst);
+int mfb_stage_out(mfb_ctx* ctx, const void* dev_src, size_t bytes, void* dst);
+
+// mfb_pattern.cu
+int mfb_build_permutation(mfb_ctx* ctx);
+int mfb_build_pattern(mfb_ctx* ctx);
+int mfb_to_internal(mfb_ctx* ctx, const double* ref_vec, double* int_vec, int levels);    // device ptrs
+int mfb_to_reference(mfb_ctx* ctx, const double* int_vec, double* ref_vec, int levels);  // device ptrs
+int mfb_field_to_internal(mfb_ctx* ctx, const double* ref_field, double* int_field);
+int mfb_export_matrix(mfb_ctx* ctx, const double* Kint, double* Kref_dev);
+int mfb_export_pattern(mfb_ctx* ctx, int* K_I, int* K_J, int* K_J_ptr, int* K_val_ids);  // device ptrs (nullable)
+
+// mfb_krylov.cu
+int mfb_spmv_internal(mfb_ctx* ctx, const double* K, const double* x, double* y);
