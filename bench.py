@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- Newton-step benchmark of the MetaFEM hot path on B200 (see DESIGN.md "Measurement").
+
+One *step* = one Newton iteration of the reference's update_OneStep! loop (src/solver/04_Time_Domain.jl:66-77)
+on the hyper-elastic box of BASELINE.json configs[2] (Neo-Hookean, hex20, 27 Gauss points):
+    update_x_star! -> K_nonlinear_func (residual + tangent assembly) -> normalized_norm(residue)
+    -> linear_solver (bicgstabl_GS!, right Jacobi, to the script's tolerance) -> update_dx!
+Every step starts from the same seeded state, so all K timed steps do identical work.
+`value`  : DOF/s with the state resident in HBM.
+`e2e`    : same metric through the public API with HOST buffers: x (pinned) H2D and dx D2H inside the timed region.
+`roofline`: the dominant kernel of the step (block SpMV of the Krylov loop), timed live with CUDA events.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--n", type=int, default=88, help="elements per box side (88 -> 8.39M DOF)")
+    p.add_argument("--cpu-n", type=int, default=20, help="elements per side of the bounded CPU-baseline sample")
+    p.add_argument("--numbering", default="scattered", choices=["scattered", "sorted"])
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+# ---- workload definition (examples/hyper_elasticity/static_Neo_Hookean.jl, setups[1]) -------------------------
+MU, LAM, LOAD, TOL = 1e6, 1e6, 4e5, 1e-5
+SOLVER = dict(Sv_func="bicgstabl_GS", maxiter=3000, max_pass=10, s=4)
+
+
+def initial_state(x, h, seed=1234):
+    """Smooth displacement + uniform noise of +-1e-3 h (keeps det F > 0); SURVEY.md §8(d)."""
+    rng = np.random.default_rng(seed)
+    N = x.shape[1]
+    d = [0.02 * np.sin(1.3 * x[(i + 1) % 3] + 0.2 * i) * x[0] + rng.uniform(-1e-3, 1e-3, N) * h for i in range(3)]
+    return d
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([s.strip() for s in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.25)
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        if not rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        sm = sorted(int(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=int(rows[0][1]), reasons=reasons, samples=len(rows))
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class CpuReference:
+    """The reference's algorithm (oracle port: term-by-term _Var/_Res/_Kval loops over pre-tabulated integral_vals,
+    CSR SpMV, bicgstabl_GS!) on the host cores, on a bounded sample of the same workload."""
+
+    def __init__(self, n_side, threads=None):
+        from oracle import refgeom as rg, femmesh as fm, assembly as oasm, solver as osv, cpath
+        import metafem_b200  # noqa: F401
+        from metafem_jl_b200.frontend import weakform as wf
+        self.threads = threads or os.cpu_count()
+        cpath.set_threads(self.threads)
+        self.n_side = n_side
+        size, n = (1.0, 1.0, 1.0), (n_side,) * 3
+        c, conn = rg.make_Brick(size, n, "CUBE")
+        m = rg.construct_TotalMesh_3D(c, conn)
+        fids = rg.get_BoundaryMesh(m)
+        cen = rg.face_centroids(m, fids)
+        mesh = fm.mesh_Classical(m, [fids[np.abs(cen[0]) < 1e-9], fids[np.abs(cen[0] - 1.0) < 1e-9]], "CUBE")
+        fm.update_Mesh(mesh)
+        dom = oasm.Domain(mesh, wf.neo_hookean(fixed_bg=1, traction_bg=2))
+        dom.global_vars.update(mu=MU, lam=LAM, tau_b=1000 * max(MU, LAM))
+        for b, v in zip(("d1", "d2", "d3"), initial_state(mesh.x, 1.0 / n_side)):
+            dom.cp[b][:] = v
+        dom.cp["Pl1"][:] = LOAD
+        dom.globalfield.converge_tol = TOL
+        oasm.assemble_Global_Variables(dom)
+        osv.update_Time(dom)
+        oasm.K_linear_func(dom)
+        self.dom, self.oasm, self.osv = dom, oasm, osv
+        self.ndof = dom.globalfield.basicfield_size
+
+    def step(self):
+        from threadpoolctl import threadpool_limits
+        dom, oasm, osv = self.dom, self.oasm, self.osv
+        with threadpool_limits(limits=1, user_api="blas"):   # OpenBLAS's spinning threads fight the OpenMP team otherwise
+            t0 = time.perf_counter()
+            osv.initialize_dx(dom)
+            osv.update_x_star(dom)
+            oasm.K_nonlinear_func(dom)
+            t_asm = time.perf_counter() - t0
+            res = osv.normalized_norm(dom.globalfield.residue)
+            delta = osv.iterative_Solve(dom, osv.bicgstabl_GS, max_pass=SOLVER["max_pass"], maxiter=SOLVER["maxiter"],
+                                        s=SOLVER["s"])
+            osv.update_dx(dom, -delta)
+            t = time.perf_counter() - t0
+        return dict(value=self.ndof / t, unit="DOF/s", cores=self.threads, kind="port",
+                    sample=f"one Newton step of the same Neo-Hookean hex20 box at {self.n_side}^3 elements ({self.ndof} DOF): "
+                           f"{t:.2f} s total, assembly {t_asm:.2f} s, {sum(dom.last_solve['iters'])} Krylov iterations, "
+                           f"initial residual {res:.3e}"), t
+
+
+def cpu_baseline(n_side):
+    return CpuReference(n_side).step()[0]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    ref = CpuReference(args.cpu_n)
+    ts = []
+    for i in range(W + K):
+        cb, t = ref.step()
+        if i >= W:
+            ts.append(t)
+    ms = float(np.mean(ts)) * 1e3
+    v = ref.ndof / (ms * 1e-3)
+    cb["value"] = v
+    print(json.dumps({"impl": "reference", "metric": "newton_step_dof_per_s", "value": v, "unit": "DOF/s",
+                      "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": workload_config(args, sample_n=args.cpu_n), "cpu_baseline": cb,
+                      "e2e": {"value": v, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def workload_config(args, sample_n=None, extra=None):
+    n = sample_n or args.n
+    cfg = {"workload": "examples/hyper_elasticity: Neo-Hookean Newton step, hex20 x 27 Gauss points, "
+                       f"unit box {n}^3 elements (BASELINE configs[2]; 88^3 = 8.39M DOF)",
+           "mu": MU, "lambda": LAM, "traction": LOAD, "converge_tol": TOL,
+           "solver": f"{SOLVER['Sv_func']} s={SOLVER['s']} maxiter={SOLVER['maxiter']} max_pass={SOLVER['max_pass']}, right Jacobi",
+           "midedge_numbering": args.numbering,
+           "cache": "inputs larger than L2 (matrix values alone exceed 126 MB); no explicit flush"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    import metafem_b200 as m
+    from metafem_jl_b200.frontend import weakform as wf, mesh as fmesh
+    L = m.lib
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    K, W = args.steps, max(args.warmup, 0)
+
+    # ---- setup (untimed): mesh tables, pattern, kernels ---------------------------------------------------------
+    # replicas-only multi-GPU in this round: every rank runs the same box (weak scaling, no data-path collective)
+    t_setup = time.perf_counter()
+    n = args.n
+    tables = fmesh.box_tables((1.0, 1.0, 1.0), (n, n, n), "CUBE", groups=("left", "right"), numbering=args.numbering)
+    spec = wf.neo_hookean(fixed_bg=1, traction_bg=2)
+    fd = m.FEM_Domain(tables, spec, device=local)
+    stream = torch.cuda.Stream()
+    fd.ctx.call("mfb_set_stream", L.ptr(stream.cuda_stream))
+    for b, v in zip(("d1", "d2", "d3"), initial_state(tables.x, 1.0 / n)):
+        fd.controlpoints[b][:] = v
+    fd.controlpoints["Pl1"][:] = LOAD
+    fd.global_vars.update(mu=MU, lam=LAM, tau_b=1000 * max(MU, LAM))
+    fd.globalfield.converge_tol = TOL
+    m.assemble_Global_Variables(fd)
+    m.compile_Updater_GPU(1, fd)
+    gf, td = fd.globalfield, fd.time_discretization
+    m.api.update_Time(gf, td)
+    ndof, nnz = gf.basicfield_size, gf.nnz
+    kp = np.array(td.K_params); alpha = np.array(td.alpha_params); beta = np.array(td.beta_params)
+    gam = np.array(td.gamma_params)
+    fd.sync_fields()
+    fd.ctx.call("mfb_assemble_linear", L.ptr(kp), len(kp))        # K_linear_func: once per time step, outside the Newton loop
+    x_host = torch.empty(ndof, dtype=torch.float64).pin_memory()
+    x_host.numpy()[:] = fd.get_vector(L.VEC_X)
+    dx_host = torch.empty(ndof, dtype=torch.float64).pin_memory()
+    t_setup = time.perf_counter() - t_setup
+    import ctypes as C
+    info = L.SolveInfo()
+    res = C.c_double(0.0)
+
+    def step(e2e):
+        if e2e:
+            fd.ctx.call("mfb_vector_set", L.VEC_X, L.ptr(x_host), ndof)
+        fd.ctx.call("mfb_initialize_dx", gf.dt, L.ptr(gam), len(gam))
+        fd.ctx.call("mfb_update_x_star", L.ptr(alpha), len(alpha))
+        fd.ctx.call("mfb_assemble_nonlinear", L.ptr(kp), len(kp), gf.t, gf.dt)
+        fd.ctx.call("mfb_residue_norm", C.byref(res))
+        fd.ctx.call("mfb_krylov_solve", L.MFB_BICGSTABL_GS, SOLVER["s"], SOLVER["maxiter"], SOLVER["max_pass"], TOL, 1234,
+                    None, C.byref(info))
+        fd.ctx.call("mfb_update_dx", L.ptr(beta), len(beta), -1.0)
+        if e2e:
+            fd.ctx.call("mfb_vector_get", L.VEC_DX, L.ptr(dx_host), ndof)
+
+    def timed(e2e, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record()
+            for _ in range(steps):
+                step(e2e)
+            e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(W, 3)):
+            step(False)
+    torch.cuda.synchronize()
+    # ---- timed region: resident inputs ------------------------------------------------------------------------
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = fd.ctx.lib.mfb_launch_count(fd.ctx.h)
+    fd.ctx.call("mfb_profile_enable", 1)
+    ms_total = timed(False, K)
+    launches = fd.ctx.lib.mfb_launch_count(fd.ctx.h) - l0
+    pms = (C.c_double * 8)(); pcnt = (C.c_int64 * 8)()
+    fd.ctx.call("mfb_profile_get", pms, pcnt)
+    fd.ctx.call("mfb_profile_enable", 0)
+    # ---- timed region: end to end (host buffers) ------------------------------------------------------------
+    ms_e2e = timed(True, K)
+    clk = clocks.stop()
+    if rank != 0:
+        return
+    ms_step = ms_total / K
+    value = world * ndof / (ms_step * 1e-3)
+    e2e_val = world * ndof / (ms_e2e / K * 1e-3)
+    peak, peak_kind = hbm_peak()
+    spmv_ms = pms[0] / max(pcnt[0], 1)
+    spmv_bytes = 12.0 * nnz + 4.0 * (ndof + 1) + 16.0 * ndof
+    achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+    asm_ms = pms[1] / max(pcnt[1], 1)
+    elem_ms = pms[4] / max(pcnt[4], 1)
+    n_el = n ** 3
+    asm_bytes = 8.0 * nnz + 8.0 * ndof + 8.0 * ndof + 24.0 * tables.variable_size + 4.0 * 20 * n_el + 4.0 * 400 * n_el
+    out = {
+        "metric": "newton_step_dof_per_s", "value": value, "unit": "DOF/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(args, extra={
+            "dof": ndof, "nnz": nnz, "elements": n_el, "parallelism": "replicas only" if world > 1 else "single GPU",
+            "krylov_iterations_per_step": info.iterations, "spmv_per_step": info.spmv_count, "passes": info.passes,
+            "solver_converged": bool(info.converged), "initial_residual": res.value, "final_residual": info.residual,
+            "setup_s": t_setup}),
+        "newton_step_ms": ms_step, "assembly_ms": asm_ms, "assembly_dof_per_s": ndof / (asm_ms * 1e-3),
+        "element_kernel_ms": elem_ms, "solve_ms": pms[3] / max(pcnt[3], 1), "spmv_ms": spmv_ms,
+        "spmv_share_of_step": pms[0] / ms_total,
+        "roofline": {"bound": "hbm", "kernel": "k_spmv_bsr<3>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                     "algorithmic_bytes": spmv_bytes, "launches_timed": int(pcnt[0]), "avg_ms": spmv_ms},
+        "roofline_assembly": {"bound": "fp64", "kernel": "mfb_b0_nl (fused element kernel)", "avg_ms": elem_ms,
+                              "hbm_algorithmic_bytes": asm_bytes, "hbm_frac": asm_bytes / (elem_ms * 1e-3) / 1e9 / peak,
+                              "flops_model": 2.62e6 * n_el, "tflops": 2.62e6 * n_el / (elem_ms * 1e-3) / 1e12},
+        "e2e": {"value": e2e_val, "unit": "DOF/s", "h2d_bytes_per_step": 8 * ndof, "d2h_bytes_per_step": 8 * ndof + 8,
+                "ms_per_step": ms_e2e / K},
+        "gpu_launches": int(launches), "clocks": clk,
+    }
+    if not args.no_cpu_baseline:
+        try:
+            out["cpu_baseline"] = cpu_baseline(args.cpu_n)
+        except Exception as e:  # the baseline is a reported number, never a reason to lose the GPU measurement
+            out["cpu_baseline"] = {"value": None, "unit": "DOF/s", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"failed: {type(e).__name__}: {e}"}
+    print(json.dumps(out))
+    fd.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

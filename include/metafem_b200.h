@@ -54,6 +54,11 @@ int mfb_set_stream(mfb_ctx *ctx, void *cuda_stream);
 /* number of kernels this library has launched on ctx since creation (bench.py "gpu_launches") */
 int64_t mfb_launch_count(mfb_ctx *ctx);
 int mfb_synchronize(mfb_ctx *ctx);
+/* CUDA-event timers on the context's stream. ids: 0 SpMV, 1 K_nonlinear_func, 2 K_linear_func,
+ * 3 Krylov solve, 4 domain element kernel, 7 boundary element kernels. mfb_profile_get sums and
+ * clears them: ms[8], count[8]. */
+int mfb_profile_enable(mfb_ctx *ctx, int on);
+int mfb_profile_get(mfb_ctx *ctx, double *ms, int64_t *count);
 
 /* ---- mesh tables ---------------------------------------------------------------------
  * Replaces the element tables produced by mesh_Classical + update_Mesh

@@ -66,6 +66,12 @@ struct BoundaryGroup {
 
 struct Comm;  // mfb_dist.cu
 
+// CUDA-event timers on the context's stream (bench.py roofline numbers); ids = MFB_T_*
+enum { MFB_T_SPMV = 0, MFB_T_ASM_NONLINEAR = 1, MFB_T_ASM_LINEAR = 2, MFB_T_SOLVE = 3, MFB_T_ELEM_KERNEL = 4, MFB_T_COUNT = 8 };
+struct ProfEvents {
+    std::vector<cudaEvent_t> start, stop;
+};
+
 struct mfb_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -119,6 +125,32 @@ struct mfb_ctx {
     DevBuf<unsigned char> stage;
 
     Comm* comm = nullptr;
+
+    // ---- profiling ----
+    bool profile = false;
+    ProfEvents prof[MFB_T_COUNT];
+    double prof_ms[MFB_T_COUNT] = {0};
+    int64_t prof_n[MFB_T_COUNT] = {0};
+};
+
+struct ProfScope {
+    mfb_ctx* c;
+    int id;
+    bool on;
+    ProfScope(mfb_ctx* ctx, int id_) : c(ctx), id(id_), on(ctx->profile) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, c->stream);
+        c->prof[id].start.push_back(e);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, c->stream);
+        c->prof[id].stop.push_back(e);
+    }
 };
 
 // staging: returns a device-readable pointer for `src` (device/unified/pinned pass through; pageable host is copied)

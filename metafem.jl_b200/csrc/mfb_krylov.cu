@@ -217,6 +217,7 @@ __global__ void k_div(double* y, const double* x, const double* d, int64_t n) {
 int mfb_spmv_internal(mfb_ctx* ctx, const double* K, const double* x, double* y) {
     const int64_t N = ctx->N;
     unsigned grid = (unsigned)((N * 32 + 255) / 256);
+    ProfScope ps(ctx, MFB_T_SPMV);
     switch (ctx->n_var) {
         case 1: LAUNCH(k_spmv_bsr<1>, grid, 256, ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N); break;
         case 2: LAUNCH(k_spmv_bsr<2>, grid, 256, ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N); break;
@@ -504,6 +505,7 @@ extern "C" int mfb_krylov_solve(mfb_ctx* ctx, int method, int s, int maxiter, in
     MFB_REQUIRE(s >= 1 && 3 * s + 4 <= MAXT && s <= MAXD, MFB_ERR_ARG, "s out of range");
     MFB_CUDA(cudaSetDevice(ctx->device));
     MFB_TRY(ensure_scalars(ctx));
+    ProfScope ps(ctx, MFB_T_SOLVE);
     const int nv = ctx->n_var;
     const int64_t n = ctx->N * nv;
     const int64_t nval = ctx->U * nv * nv;

@@ -41,6 +41,8 @@ _SIGS = {
     "mfb_set_stream": (C.c_int, [_P, _P]),
     "mfb_launch_count": (C.c_int64, [_P]),
     "mfb_synchronize": (C.c_int, [_P]),
+    "mfb_profile_enable": (C.c_int, [_P, C.c_int]),
+    "mfb_profile_get": (C.c_int, [_P, _P, _P]),
     "mfb_mesh_set": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, C.c_int, _P, _P, _P, _P, _P, _P]),
     "mfb_facets_set": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.c_int64, _P, _P]),
     "mfb_boundary_group_set": (C.c_int, [_P, C.c_int, C.c_int64, _P]),

@@ -10,6 +10,7 @@ expressions are evaluated with numpy here. All stored IDs are 1-based like the r
 import numpy as np
 
 from .femdict import FemDict, I32I32_To_UI64, UI64_To_UpperHalf, UI64_To_LowerHalf
+from . import cpath
 
 _NS = dict(pow=np.power, log=np.log, exp=np.exp, sqrt=np.sqrt, fabs=np.abs)
 
@@ -145,13 +146,19 @@ def _block_context(dom, blk):
     if blk["kind"] == "domain":
         n_el = mesh.controlpoint_IDs.shape[1]
         el = np.arange(n_el)
-        return el, mesh.integral_vals, mesh.integral_weights, None
+        return Ctx(el, el, mesh.integral_vals, mesh.integral_weights, None)
     f = mesh.bg_fIDs[blk["bg_ID"]] - 1
     el = mesh.facet_element_ID[f] - 1
-    return el, mesh.facet_integral_vals[f], mesh.facet_integral_weights[f], mesh.facet_normal_directions[f]
+    return Ctx(el, f, mesh.facet_integral_vals, mesh.facet_integral_weights[f], mesh.facet_normal_directions[f])
 
 
-def _declare_vars(dom, blk, el, iv, normals, which):
+class Ctx:
+    """elIDs, local_itg_hostIDs, local_integral_vals, weights[:, hostIDs], normals of one block."""
+    def __init__(self, el, host, itp, w, normals):
+        self.el, self.host, self.itp, self.w, self.normals = el, host, np.ascontiguousarray(itp), w, normals
+
+
+def _declare_vars(dom, blk, cx, which):
     """declare_Innervar_GPU / declare_Extervar_GPU (:1-50): _Var_Basic per word."""
     mesh, gf = dom.mesh, dom.globalfield
     N = mesh.variable_size
@@ -159,16 +166,15 @@ def _declare_vars(dom, blk, el, iv, normals, which):
     if which != "linear":
         for w in blk["innervars"]:
             shift = w["td"] * gf.basicfield_size + w["pos"] * N
-            ids = mesh.global_cpIDs[:, el] - 1 + shift                      # (a, e)
-            env[w["sym"]] = np.einsum("eaq,ae->eq", iv[:, sd_slot(w["sd"])], gf.x_star[ids])
+            env[w["sym"]] = cpath.var_basic(cx.itp, sd_slot(w["sd"]), shift, mesh.global_cpIDs, cx.el, cx.host, gf.x_star)
     for w in blk["extervars"]:
         if w["kind"] == "global":
             env[w["sym"]] = gf.t if w["sym"] == "t" else gf.dt if w["sym"] == "dt" else dom.global_vars[w["sym"]]
         elif w["kind"] == "cp":
-            ids = mesh.controlpoint_IDs[:, el] - 1
-            env[w["sym"]] = np.einsum("eaq,ae->eq", iv[:, sd_slot(w["sd"])], dom.cp[w["local"]][ids])
+            env[w["sym"]] = cpath.var_basic(cx.itp, sd_slot(w["sd"]), 0, mesh.controlpoint_IDs, cx.el, cx.host,
+                                            np.ascontiguousarray(dom.cp[w["local"]]))
         elif w["kind"] == "normal":
-            env[w["sym"]] = normals[:, w["c"] - 1, :]
+            env[w["sym"]] = cx.normals[:, w["c"] - 1, :]
     return env
 
 
@@ -186,13 +192,23 @@ def _temps(blk, env, needed_inner):
                 raise
 
 
-def _kval(dom, K, term, vals, el, iv):
-    """_Kval_Basic (06_FEM_Kernel.jl:28-45)."""
+def _kval(dom, K, term, vals, cx):
+    """_Kval_Basic (06_FEM_Kernel.jl:28-45); loop nest in c/refpath.c."""
     mesh = dom.mesh
     m = dom.spec["sparse_mapping"].index([term["dual_pos"], term["deriv_pos"]])
     shift = m * mesh.sparse_unitsize
+    cpath.kval_basic(cx.itp, sd_slot(term["dual_sd"]), sd_slot(term["deriv_sd"]), vals, mesh.sparse_IDs_by_el, shift,
+                     cx.el, cx.host, K)
+
+
+def _kval_numpy(dom, K, term, vals, cx):
+    """Same contraction with numpy (cross-check of the C loop nest in tests)."""
+    mesh = dom.mesh
+    m = dom.spec["sparse_mapping"].index([term["dual_pos"], term["deriv_pos"]])
+    shift = m * mesh.sparse_unitsize
+    iv = cx.itp[cx.host]
     Ke = np.einsum("eaq,ebq,eq->abe", iv[:, sd_slot(term["dual_sd"])], iv[:, sd_slot(term["deriv_sd"])], vals)
-    np.add.at(K, mesh.sparse_IDs_by_el[:, :, el] - 1 + shift, Ke)
+    np.add.at(K, mesh.sparse_IDs_by_el[:, :, cx.el] - 1 + shift, Ke)
 
 
 def K_linear_func(dom):
@@ -202,12 +218,12 @@ def K_linear_func(dom):
     for blk in dom.spec["blocks"]:
         if not blk["linear_gradients"]:
             continue
-        el, iv, w, normals = _block_context(dom, blk)
-        env = _declare_vars(dom, blk, el, iv, normals, "linear")
+        cx = _block_context(dom, blk)
+        env = _declare_vars(dom, blk, cx, "linear")
         _temps(blk, env, False)
         for term in blk["linear_gradients"]:
-            vals = _eval(term["expr"], env, w.shape) * dom.K_params[term["deriv_td"]] * w
-            _kval(dom, gf.K_linear, term, vals, el, iv)
+            vals = _eval(term["expr"], env, cx.w.shape) * dom.K_params[term["deriv_td"]] * cx.w
+            _kval(dom, gf.K_linear, term, vals, cx)
 
 
 def K_nonlinear_func(dom):
@@ -217,16 +233,22 @@ def K_nonlinear_func(dom):
     gf.residue[:] = 0.0
     gf.K_total[:] = gf.K_linear
     for blk in dom.spec["blocks"]:
-        el, iv, w, normals = _block_context(dom, blk)
-        env = _declare_vars(dom, blk, el, iv, normals, "nonlinear")
+        cx = _block_context(dom, blk)
+        env = _declare_vars(dom, blk, cx, "nonlinear")
         _temps(blk, env, True)
         for term in blk["residues"]:
-            vals = _eval(term["expr"], env, w.shape) * w
-            r = np.einsum("eaq,eq->ae", iv[:, sd_slot(term["dual_sd"])], vals)      # _Res_Basic :65-79
-            np.add.at(gf.residue, mesh.global_cpIDs[:, el] - 1 + term["dual_pos"] * N, r)
+            vals = _eval(term["expr"], env, cx.w.shape) * cx.w
+            cpath.res_basic(cx.itp, sd_slot(term["dual_sd"]), vals, term["dual_pos"] * N, mesh.global_cpIDs,
+                            cx.el, cx.host, gf.residue)                                  # _Res_Basic :65-79
         for term in blk["nonlinear_gradients"]:
-            vals = _eval(term["expr"], env, w.shape) * dom.K_params[term["deriv_td"]] * w
-            _kval(dom, gf.K_total, term, vals, el, iv)
+            vals = _eval(term["expr"], env, cx.w.shape) * dom.K_params[term["deriv_td"]] * cx.w
+            _kval(dom, gf.K_total, term, vals, cx)
+
+
+def csr_operator(gf, K=None):
+    """K[K_val_ids] as an OpenMP CSR operator (CPU baseline)."""
+    K = gf.K_total if K is None else K
+    return cpath.CsrOperator(gf.K_J_ptr, gf.K_J, K[gf.K_val_ids - 1], gf.basicfield_size)
 
 
 def csr_from_globalfield(gf, K=None):

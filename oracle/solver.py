@@ -75,20 +75,21 @@ def update_OneStep(dom, max_iter=4, log=None):          # :59-80
 
 # ---------------------------------------------------------------------------------------------
 def Pr_Jacobi(A):
-    """Pr_Jacobi! with Jacobi_By_Diagonal + Mat_Div_Jacobi (02_Preconditioner.jl:103-148); A is scipy CSR, modified in place."""
+    """Pr_Jacobi! with Jacobi_By_Diagonal + Mat_Div_Jacobi (02_Preconditioner.jl:103-148); A: cpath.CsrOperator, modified in place."""
     n = A.shape[0]
     jac = np.ones(n)
-    rows = np.repeat(np.arange(n), np.diff(A.indptr))
-    dmask = A.indices == rows
+    rows = np.repeat(np.arange(n), np.diff(A.ptr))
+    cols = A.col - 1
+    dmask = cols == rows
     jac[rows[dmask]] = np.abs(A.data[dmask])
-    A.data /= jac[A.indices]
+    A.data /= jac[cols]
     return jac
 
 
 def iterative_Solve(dom, Sv_func, max_pass=4, seed=1234, log=None, **kw):
     """iterative_Solve! (:32-76), right Jacobi only (Pl = Identity)."""
     gf = dom.globalfield
-    A = asm.csr_from_globalfield(gf).copy()
+    A = asm.csr_operator(gf)          # K_vals = K_total[K_val_ids] (:35): a fresh copy, as in the reference
     jac = Pr_Jacobi(A)
     b = gf.residue
     r = b.copy()
