@@ -21,7 +21,7 @@ namespace {
 constexpr int TPB = 256;
 constexpr int MAXT = 48;   // max terms of one fused vector update
 constexpr int MAXD = 24;   // max dots of one fused reduction
-constexpr int RED_BLOCKS = 592;  // 4 x 148 SMs
+constexpr int RED_BLOCKS = 1184;  // 8 x 148 SMs, 256 threads each
 
 inline unsigned nblk(int64_t n) { return (unsigned)((n + TPB - 1) / TPB); }
 
@@ -33,22 +33,40 @@ __global__ void __launch_bounds__(256) k_spmv_bsr(const int* __restrict__ nodept
                                                   const double* __restrict__ K, const double* __restrict__ x,
                                                   double* __restrict__ y, int64_t N) {
     constexpr int B = NV * NV;
+    constexpr int UNR = 4;   // independent value / index / x loads in flight per lane
     const int lane = threadIdx.x & 31;
     const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (row >= N) return;
     const int s = nodeptr[row], t = nodeptr[row + 1];
     const double* Kr = K + (size_t)s * B;
+    const int* Cr = nodecol + s;
     const int nflat = (t - s) * B;
     double acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-    for (int f = lane; f < nflat; f += 32) {
-        const int ent = f / B, ik = f - ent * B;
-        const int i = ik / NV, k = ik - i * NV;
-        const double v = __ldcs(Kr + f);   // streamed once: do not displace x in L1/L2
-        const double p = v * x[(size_t)nodecol[s + ent] * NV + k];
+    for (int f0 = lane; f0 < nflat; f0 += 32 * UNR) {
+        double v[UNR];
+        int col[UNR], kk[UNR], ii[UNR];
 #pragma unroll
-        for (int ii = 0; ii < NV; ++ii) acc[ii] += (ii == i) ? p : 0.0;
+        for (int u = 0; u < UNR; ++u) {
+            const int f = f0 + 32 * u;
+            const bool ok = f < nflat;
+            const int fc = ok ? f : 0;
+            v[u] = ok ? __ldcs(Kr + fc) : 0.0;   // streamed once: keep x resident in L1/L2 instead
+            const int ent = fc / B, ik = fc - ent * B;
+            ii[u] = ik / NV;
+            kk[u] = ik - ii[u] * NV;
+            col[u] = __ldg(Cr + ent);
+        }
+        double xv[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) xv[u] = __ldg(x + (size_t)col[u] * NV + kk[u]);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const double p = v[u] * xv[u];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) acc[i] += (i == ii[u]) ? p : 0.0;
+        }
     }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -101,14 +119,32 @@ struct LinComb {
     const double* x[MAXT];
 };
 
-// optional fused squared norm of the result (partials[block])
+// optional fused squared norm of the result (partials[block]); 4 independent elements per thread for memory-level parallelism
 __global__ void __launch_bounds__(TPB) k_lincomb(LinComb L, int64_t n, double* partial_norm2) {
     double nrm = 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double s = (L.ay != 0.0) ? L.ay * L.y[i] : 0.0;
-        for (int k = 0; k < L.n; ++k) s += L.c[k] * L.x[k][i];
-        L.y[i] = s;
-        nrm += s * s;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        double sv[4];
+        int64_t idx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            idx[u] = i0 + u * stride;
+            if (idx[u] >= n) idx[u] = -1;
+            sv[u] = (L.ay != 0.0 && idx[u] >= 0) ? L.ay * L.y[idx[u]] : 0.0;
+        }
+        for (int k = 0; k < L.n; ++k) {
+            const double c = L.c[k];
+            const double* __restrict__ xp = L.x[k];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (idx[u] >= 0) sv[u] += c * xp[idx[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (idx[u] >= 0) {
+                L.y[idx[u]] = sv[u];
+                nrm += sv[u] * sv[u];
+            }
     }
     if (partial_norm2) {
         __shared__ double sh[TPB / 32];
@@ -131,8 +167,18 @@ struct AxpbyBatch {
 };
 // y_k = a_k*y_k + b_k*x_k for k < n, independent updates in one launch
 __global__ void __launch_bounds__(TPB) k_axpby_batch(AxpbyBatch Bt, int64_t n) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        for (int k = 0; k < Bt.n; ++k) Bt.y[k][i] = Bt.a[k] * Bt.y[k][i] + Bt.b[k] * Bt.x[k][i];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < n; i0 += 2 * stride) {
+        const int64_t i1 = i0 + stride;
+        const bool ok1 = i1 < n;
+        for (int k = 0; k < Bt.n; ++k) {
+            double* __restrict__ yp = Bt.y[k];
+            const double* __restrict__ xp = Bt.x[k];
+            const double y0 = yp[i0], x0 = xp[i0];
+            const double y1 = ok1 ? yp[i1] : 0.0, x1 = ok1 ? xp[i1] : 0.0;
+            yp[i0] = Bt.a[k] * y0 + Bt.b[k] * x0;
+            if (ok1) yp[i1] = Bt.a[k] * y1 + Bt.b[k] * x1;
+        }
     }
 }
 
@@ -147,10 +193,17 @@ __global__ void __launch_bounds__(TPB) k_multidot(MultiDot M, int64_t n, double*
     for (int k0 = 0; k0 < M.n; k0 += 4) {
         double acc[4] = {0, 0, 0, 0};
         const int nk = min(4, M.n - k0);
-        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
+            const int64_t i1 = i + stride;
+            const bool ok1 = i1 < n;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (k < nk) acc[k] += M.x[k0 + k][i] * M.y[k0 + k][i];
+                if (k < nk) {
+                    const double a0 = M.x[k0 + k][i], b0 = M.y[k0 + k][i];
+                    const double a1 = ok1 ? M.x[k0 + k][i1] : 0.0, b1 = ok1 ? M.y[k0 + k][i1] : 0.0;
+                    acc[k] += a0 * b0 + a1 * b1;
+                }
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
