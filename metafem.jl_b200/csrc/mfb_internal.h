@@ -83,7 +83,9 @@ struct mfb_ctx {
     int n_a = 0, n_q = 0, n_faces = 0, n_qb = 0;
     int64_t n_el = 0, N = 0, n_facets = 0;
     DevBuf<int> conn_ref;     // [n_el][n_a] 0-based reference node ids
-    DevBuf<int> conn;         // [n_el][n_a] internal node ids
+    DevBuf<int> conn;         // [n_el][n_a] internal node ids, elements in internal (Morton) order
+    DevBuf<int> elem_order;   // elem_order[internal element] = reference element (0-based)
+    DevBuf<int> elem_rank;    // inverse
     DevBuf<double> xyz;       // [N][3] internal order
     DevBuf<double> ref, wq;   // domain tables [4][n_q][n_a], [n_q]
     DevBuf<double> bref, bwq, btan;  // boundary tables per face
@@ -158,7 +160,7 @@ int mfb_stage_in(mfb_ctx* ctx, const void* src, size_t bytes, void* dev_dst);
 int mfb_stage_out(mfb_ctx* ctx, const void* dev_src, size_t bytes, void* dst);
 
 // mfb_pattern.cu
-int mfb_build_permutation(mfb_ctx* ctx);
+int mfb_build_permutation(mfb_ctx* ctx, const double* x1, const double* x2, const double* x3);
 int mfb_build_pattern(mfb_ctx* ctx);
 int mfb_to_internal(mfb_ctx* ctx, const double* ref_vec, double* int_vec, int levels);    // device ptrs
 int mfb_to_reference(mfb_ctx* ctx, const double* int_vec, double* ref_vec, int levels);  // device ptrs

@@ -26,10 +26,86 @@ constexpr int RED_BLOCKS = 1184;  // 8 x 148 SMs, 256 threads each
 inline unsigned nblk(int64_t n) { return (unsigned)((n + TPB - 1) / TPB); }
 
 // ---------------------------------------------------------------------------------------------
-// SpMV: one warp per block row; the row's values are read as ONE flat coalesced stream of
-// deg*NV*NV doubles (lane f handles value f: entry f/(NV*NV), block row i, block column k).
+// SpMV (main kernel, NV*NV <= 32). One warp per block row, 8 warps walk a contiguous chunk of SPMV_ROWS rows.
+//  * Lane l owns ONE fixed position (i,k) of the NV x NV block and steps through the row EPW = 32/(NV*NV) entries at a
+//    time: consecutive lanes read consecutive doubles (a fully coalesced stream of the row's values), (i,k) and the x
+//    component never change per lane, so per value the lane issues 3 loads + 1 DFMA and nothing else.
+//  * The loop is software-pipelined: the streaming loads (values, column ids) of batch j+1 are issued BEFORE the
+//    dependent x gathers of batch j are consumed, and the next row's pointers are fetched one row ahead. The round-1
+//    kernel had the chain nodeptr -> (vals, cols) -> x[col] exposed on every batch and sat at 46 % of DRAM peak;
+//    measured on the real 88^3 pattern: 3.16 ms -> 2.26 ms (profiles/exp/spmv_exp2.cu, profiles/spmv_experiments_r1.md).
+//  * Values are streamed with evict-first loads so x stays resident in L1/L2; the Morton node order keeps the gathers local.
+constexpr int SPMV_ROWS = 64;
+template <int NV> struct SpmvUnroll { static constexpr int value = NV == 1 ? 2 : NV == 2 ? 3 : NV == 3 ? 5 : NV == 4 ? 6 : 8; };
+
 template <int NV>
 __global__ void __launch_bounds__(256) k_spmv_bsr(const int* __restrict__ nodeptr, const int* __restrict__ nodecol,
+                                                  const double* __restrict__ K, const double* __restrict__ x,
+                                                  double* __restrict__ y, int64_t N) {
+    constexpr int B = NV * NV;
+    constexpr int EPW = 32 / B;        // entries per warp step
+    constexpr int ACTIVE = EPW * B;    // active lanes (27 of 32 for NV = 3)
+    constexpr int UNR = SpmvUnroll<NV>::value;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int le = lane / B, ik = lane - le * B, i = ik / NV, k = ik - i * NV;
+    const double* xk = x + k;
+    const int64_t row0 = blockIdx.x * (int64_t)SPMV_ROWS + warp;
+    const int64_t rend = min((blockIdx.x + 1) * (int64_t)SPMV_ROWS, N);
+    if (row0 >= rend) return;
+    int ps = nodeptr[row0], pt = nodeptr[row0 + 1];
+    for (int64_t row = row0; row < rend; row += 8) {
+        const int s = ps, deg = (lane < ACTIVE) ? pt - ps : 0;
+        if (row + 8 < rend) { ps = __ldg(nodeptr + row + 8); pt = __ldg(nodeptr + row + 9); }
+        const double* Kp = K + (size_t)s * B + lane;
+        const int* Cp = nodecol + s + le;
+        double a[UNR], v[UNR];
+        int c[UNR];
+        int e = le;
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            a[u] = 0.0;
+            const bool ok = e + u * EPW < deg;
+            v[u] = ok ? __ldcs(Kp + u * ACTIVE) : 0.0;
+            c[u] = ok ? __ldg(Cp + u * EPW) : 0;
+        }
+        while (e < deg) {
+            double vn[UNR];
+            int cn[UNR];
+            e += UNR * EPW;
+            Kp += UNR * ACTIVE;
+            Cp += UNR * EPW;
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const bool ok = e + u * EPW < deg;
+                vn[u] = ok ? __ldcs(Kp + u * ACTIVE) : 0.0;
+                cn[u] = ok ? __ldg(Cp + u * EPW) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) a[u] += v[u] * __ldg(xk + (size_t)c[u] * NV);
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) { v[u] = vn[u]; c[u] = cn[u]; }
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) acc += a[u];
+        double t = acc;
+#pragma unroll
+        for (int d = 1; d < NV; ++d) t += __shfl_down_sync(0xffffffffu, acc, d);          // sum over k
+        double r = t;
+        if constexpr ((B & (B - 1)) == 0) {                                                // EPW is a power of two: butterfly
+#pragma unroll
+            for (int o = 16; o >= B; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        } else {
+#pragma unroll
+            for (int d = 1; d < EPW; ++d) r += __shfl_down_sync(0xffffffffu, t, d * B);   // sum over the EPW entries
+        }
+        if (le == 0 && k == 0 && lane < ACTIVE) y[(size_t)row * NV + i] = r;
+    }
+}
+
+// SpMV (fallback, any NV): the row's values as one flat stream, (entry, i, k) recomputed per value.
+template <int NV>
+__global__ void __launch_bounds__(256) k_spmv_bsr_flat(const int* __restrict__ nodeptr, const int* __restrict__ nodecol,
                                                   const double* __restrict__ K, const double* __restrict__ x,
                                                   double* __restrict__ y, int64_t N) {
     constexpr int B = NV * NV;
@@ -269,7 +345,8 @@ __global__ void k_div(double* y, const double* x, const double* d, int64_t n) {
 // ---------------------------------------------------------------------------------------------
 int mfb_spmv_internal(mfb_ctx* ctx, const double* K, const double* x, double* y) {
     const int64_t N = ctx->N;
-    unsigned grid = (unsigned)((N * 32 + 255) / 256);
+    unsigned grid = (unsigned)((N + SPMV_ROWS - 1) / SPMV_ROWS);
+    const unsigned gridf = (unsigned)((N * 32 + 255) / 256);
     ProfScope ps(ctx, MFB_T_SPMV);
     switch (ctx->n_var) {
         case 1: LAUNCH(k_spmv_bsr<1>, grid, 256, ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N); break;
@@ -277,7 +354,7 @@ int mfb_spmv_internal(mfb_ctx* ctx, const double* K, const double* x, double* y)
         case 3: LAUNCH(k_spmv_bsr<3>, grid, 256, ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N); break;
         case 4: LAUNCH(k_spmv_bsr<4>, grid, 256, ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N); break;
         case 5: LAUNCH(k_spmv_bsr<5>, grid, 256, ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N); break;
-        case 6: LAUNCH(k_spmv_bsr<6>, grid, 256, ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N); break;
+        case 6: LAUNCH(k_spmv_bsr_flat<6>, gridf, 256, ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N); break;
         default: ctx->err = "n_var > 6 not supported by the block SpMV"; return MFB_ERR_ARG;
     }
     MFB_CUDA(cudaGetLastError());

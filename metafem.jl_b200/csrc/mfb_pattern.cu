@@ -11,6 +11,7 @@
 #include <thrust/binary_search.h>
 #include <thrust/device_ptr.h>
 #include <thrust/execution_policy.h>
+#include <thrust/extrema.h>
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
 #include <thrust/scan.h>
@@ -18,7 +19,9 @@
 #include <thrust/sort.h>
 #include <thrust/unique.h>
 
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "mfb_internal.h"
 
@@ -30,6 +33,52 @@ inline unsigned nblk(int64_t n) { return (unsigned)((n + TPB - 1) / TPB); }
 __global__ void k_first_touch(const int* conn_ref, int64_t n, unsigned long long* key) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) atomicMin(key + conn_ref[i], (unsigned long long)i);
+}
+
+__device__ __forceinline__ unsigned long long spread21(unsigned long long v) {   // 21 bits -> every third bit
+    v &= 0x1fffffull;
+    v = (v | v << 32) & 0x1f00000000ffffull;
+    v = (v | v << 16) & 0x1f0000ff0000ffull;
+    v = (v | v << 8) & 0x100f00f00f00f00full;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+}
+
+// Morton key of the element centroid (coordinates in reference node order), quantised to 2^bits cells per axis
+__global__ void k_elem_morton(const int* conn_ref, int n_a, int64_t n_el, const double* x1, const double* x2, const double* x3,
+                              double lo0, double lo1, double lo2, double inv0, double inv1, double inv2,
+                              unsigned long long* key, int* order) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= n_el) return;
+    double c0 = 0, c1 = 0, c2 = 0;
+    for (int a = 0; a < n_a; ++a) {
+        int g = conn_ref[e * n_a + a];
+        c0 += x1[g]; c1 += x2[g]; c2 += x3[g];
+    }
+    const double s = 1.0 / n_a, top = 2097151.0;
+    unsigned long long q0 = (unsigned long long)fmin(fmax((c0 * s - lo0) * inv0, 0.0), top);
+    unsigned long long q1 = (unsigned long long)fmin(fmax((c1 * s - lo1) * inv1, 0.0), top);
+    unsigned long long q2 = (unsigned long long)fmin(fmax((c2 * s - lo2) * inv2, 0.0), top);
+    key[e] = spread21(q0) | (spread21(q1) << 1) | (spread21(q2) << 2);
+    order[e] = (int)e;
+}
+
+// first touch in the NEW element order: key[node] = min over (new element index, local node)
+__global__ void k_first_touch_ordered(const int* conn_ref, const int* elem_order, int n_a, int64_t n_el, unsigned long long* key) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_el * n_a) return;
+    int64_t ne = i / n_a;
+    int a = (int)(i % n_a);
+    atomicMin(key + conn_ref[(int64_t)elem_order[ne] * n_a + a], (unsigned long long)i);
+}
+
+__global__ void k_renumber_ordered(const int* conn_ref, const int* elem_order, const int* perm, int n_a, int64_t n_el, int* conn) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_el * n_a) return;
+    int64_t ne = i / n_a;
+    int a = (int)(i % n_a);
+    conn[i] = perm[conn_ref[(int64_t)elem_order[ne] * n_a + a]];
 }
 
 __global__ void k_invert(const int* iperm, int64_t N, int* perm) {
@@ -170,28 +219,58 @@ __global__ void k_add1(int* p, int64_t n) {
         ctx->launches++;                                      \
     } while (0)
 
-int mfb_build_permutation(mfb_ctx* ctx) {
-    const int64_t N = ctx->N, nconn = ctx->n_el * ctx->n_a;
+// Internal numbering: elements are ordered along a Morton curve of their centroids and nodes by first touch in that
+// element order, so a row's neighbours and consecutive rows' neighbours sit close together in x (L1-resident gathers in
+// the SpMV) and neighbouring elements scatter into nearby matrix entries (L2-resident atomics in the assembly).
+// x1..x3: device pointers in REFERENCE node order. MFB_NO_PERMUTE=1 keeps the reference order (experiments).
+int mfb_build_permutation(mfb_ctx* ctx, const double* x1, const double* x2, const double* x3) {
+    const int64_t N = ctx->N, n_el = ctx->n_el, nconn = n_el * ctx->n_a;
     auto pol = thrust::cuda::par.on(ctx->stream);
     MFB_CUDA(ctx->perm.alloc(N));
     MFB_CUDA(ctx->iperm.alloc(N));
     MFB_CUDA(ctx->conn.alloc(nconn));
-    thrust::device_ptr<int> ip(ctx->iperm.p);
+    MFB_CUDA(ctx->elem_order.alloc(n_el));
+    MFB_CUDA(ctx->elem_rank.alloc(n_el));
+    thrust::device_ptr<int> ip(ctx->iperm.p), eo(ctx->elem_order.p);
     thrust::sequence(pol, ip, ip + N);
+    thrust::sequence(pol, eo, eo + n_el);
     const char* nop = getenv("MFB_NO_PERMUTE");
     if (!(nop && nop[0] == '1')) {
-        // first-touch ordering: nodes sorted by the first (element, local node) slot that references them
+        double lo[3], hi[3];
+        const double* xs[3] = {x1, x2, x3};
+        for (int d = 0; d < 3; ++d) {
+            thrust::device_ptr<const double> p(xs[d]);
+            auto mm = thrust::minmax_element(pol, p, p + N);
+            MFB_CUDA(cudaMemcpyAsync(&lo[d], thrust::raw_pointer_cast(mm.first), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            MFB_CUDA(cudaMemcpyAsync(&hi[d], thrust::raw_pointer_cast(mm.second), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+        double ext = 0.0;
+        for (int d = 0; d < 3; ++d) ext = ext > hi[d] - lo[d] ? ext : hi[d] - lo[d];
+        // same cell size on all axes, about one cell per element edge: 2^bits cells across the largest extent
+        int bits = 1;
+        while ((1ll << (3 * bits)) < n_el * 8 && bits < 21) ++bits;
+        const double inv = ext > 0 ? (double)(1ll << bits) / ext : 0.0;
+        DevBuf<unsigned long long> ekey;
+        MFB_CUDA(ekey.alloc(n_el));
+        LAUNCH(k_elem_morton, nblk(n_el), TPB, ctx->conn_ref.p, ctx->n_a, n_el, x1, x2, x3, lo[0], lo[1], lo[2], inv, inv, inv,
+               ekey.p, ctx->elem_order.p);
+        thrust::device_ptr<unsigned long long> ek(ekey.p);
+        thrust::stable_sort_by_key(pol, ek, ek + n_el, eo);
+        MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+        ekey.release();
         DevBuf<unsigned long long> key;
         MFB_CUDA(key.alloc(N));
         MFB_CUDA(cudaMemsetAsync(key.p, 0xff, N * sizeof(unsigned long long), ctx->stream));
-        LAUNCH(k_first_touch, nblk(nconn), TPB, ctx->conn_ref.p, nconn, key.p);
+        LAUNCH(k_first_touch_ordered, nblk(nconn), TPB, ctx->conn_ref.p, ctx->elem_order.p, ctx->n_a, n_el, key.p);
         thrust::device_ptr<unsigned long long> kp(key.p);
         thrust::sort_by_key(pol, kp, kp + N, ip);
         MFB_CUDA(cudaStreamSynchronize(ctx->stream));
         key.release();
     }
     LAUNCH(k_invert, nblk(N), TPB, ctx->iperm.p, N, ctx->perm.p);
-    LAUNCH(k_renumber, nblk(nconn), TPB, ctx->conn_ref.p, ctx->perm.p, nconn, ctx->conn.p);
+    LAUNCH(k_invert, nblk(n_el), TPB, ctx->elem_order.p, n_el, ctx->elem_rank.p);
+    LAUNCH(k_renumber_ordered, nblk(nconn), TPB, ctx->conn_ref.p, ctx->elem_order.p, ctx->perm.p, ctx->n_a, n_el, ctx->conn.p);
     MFB_CUDA(cudaGetLastError());
     return MFB_OK;
 }
@@ -222,6 +301,18 @@ int mfb_build_pattern(mfb_ctx* ctx) {
     LAUNCH(k_emap, nblk(total), TPB, ctx->conn.p, ctx->nodeptr.p, ctx->nodecol.p, n_a, ctx->n_el, ctx->emap.p);
     MFB_CUDA(cudaGetLastError());
     ctx->ref_pos.release();
+    if (const char* dump = getenv("MFB_DUMP_PATTERN")) {   // experiments (profiles/exp): int64 N, int64 U, nodeptr, nodecol
+        std::vector<int> hp(N + 1), hc(ctx->U);
+        MFB_CUDA(cudaMemcpy(hp.data(), ctx->nodeptr.p, (N + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+        MFB_CUDA(cudaMemcpy(hc.data(), ctx->nodecol.p, ctx->U * sizeof(int), cudaMemcpyDeviceToHost));
+        if (FILE* f = fopen(dump, "wb")) {
+            int64_t hdr[2] = {N, ctx->U};
+            fwrite(hdr, sizeof(int64_t), 2, f);
+            fwrite(hp.data(), sizeof(int), hp.size(), f);
+            fwrite(hc.data(), sizeof(int), hc.size(), f);
+            fclose(f);
+        }
+    }
     return MFB_OK;
 }
 
