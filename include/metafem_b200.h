@@ -178,6 +178,20 @@ int mfb_update_dx(mfb_ctx *ctx, const double *beta_params, int n_beta, double si
 int mfb_commit_step(mfb_ctx *ctx);
 int mfb_residue_norm(mfb_ctx *ctx, double *normalized_norm);
 
+/* ---- multi-GPU: element-block partitioning (new relative to the single-GPU reference, README.md:4) -----------
+ * One process per GPU. Each rank calls mfb_mesh_set with ITS block of elements and the nodes they touch (local
+ * numbering); matrices/residuals stay unassembled across ranks and the library completes every SpMV result,
+ * residual and Jacobi diagonal with an interface exchange-add over NCCL, and every reduction with one allreduce.
+ *   mfb_comm_unique_id: rank 0 obtains the 128-byte NCCL id and hands it to the other ranks out of band.
+ *   mfb_interface_set : neighbour ranks (ascending); offsets [n_neighbors+1] into shared_nodes; shared_nodes =
+ *                       local node IDs (1-based) shared with each neighbour, ordered identically on both sides
+ *                       (by global ID); owned [N] = 1 where this rank owns the node (lowest sharing rank);
+ *                       global_ids [N] = global node ID (1-based) of each local node. */
+int mfb_comm_unique_id(void *id128);
+int mfb_comm_init(mfb_ctx *ctx, int rank, int n_ranks, const void *id128);
+int mfb_interface_set(mfb_ctx *ctx, int n_neighbors, const int32_t *neighbor_ranks, const int64_t *offsets,
+                      const int32_t *shared_nodes, const uint8_t *owned, const int64_t *global_ids);
+
 #ifdef __cplusplus
 }
 #endif

@@ -150,6 +150,31 @@ class FEM_Domain:
         self.ctx.close()
 
 
+def comm_unique_id():
+    """128-byte NCCL id (rank 0 creates it and hands it to the other ranks, e.g. with torch.distributed.broadcast)."""
+    buf = (C.c_ubyte * 128)()
+    rc = L.load().mfb_comm_unique_id(buf)
+    if rc != 0:
+        raise L.MfbError("mfb_comm_unique_id failed: NCCL could not be loaded (set MFB_NCCL_LIB)")
+    return bytes(buf)
+
+
+def init_distributed(fem_domain, subdomain, rank, n_ranks, id_bytes):
+    """Attach a rank's FEM_Domain (built on subdomain.tables) to the NCCL communicator and register its interface."""
+    ctx = fem_domain.ctx
+    idbuf = (C.c_ubyte * 128).from_buffer_copy(id_bytes)
+    ctx.call("mfb_comm_init", int(rank), int(n_ranks), idbuf)
+    nb = _i32(subdomain.neighbors)
+    counts = [len(subdomain.shared[q]) for q in subdomain.neighbors]
+    offsets = np.ascontiguousarray(np.concatenate([[0], np.cumsum(counts)]), dtype=np.int64)
+    shared = _i32(np.concatenate([subdomain.shared[q] for q in subdomain.neighbors])) if counts else np.zeros(1, np.int32)
+    owned = np.ascontiguousarray(subdomain.owned, dtype=np.uint8)
+    gids = np.ascontiguousarray(subdomain.node_l2g, dtype=np.int64)
+    ctx.call("mfb_interface_set", len(nb), L.ptr(nb) if len(nb) else L.ptr(np.zeros(1, np.int32)), L.ptr(offsets),
+             L.ptr(shared), L.ptr(owned), L.ptr(gids))
+    fem_domain.subdomain = subdomain
+
+
 def _x_slices(dom):
     spec, gf, N = dom.spec, dom.globalfield, dom.tables.variable_size
     for pos, b in enumerate(spec["basic_vars"]):

@@ -127,6 +127,9 @@ struct mfb_ctx {
     DevBuf<unsigned char> stage;
 
     Comm* comm = nullptr;
+    DevBuf<unsigned char> owned;   // [N] internal order: 1 if this rank owns the node (all 1 on a single GPU)
+    double n_global_nodes = 0;     // number of distinct nodes over all ranks (0 = single GPU: use N)
+    DevBuf<long long> gid;         // [N] internal order: global reference node id, 0-based (seeds the shadow vectors)
 
     // ---- profiling ----
     bool profile = false;
@@ -167,6 +170,13 @@ int mfb_to_reference(mfb_ctx* ctx, const double* int_vec, double* ref_vec, int l
 int mfb_field_to_internal(mfb_ctx* ctx, const double* ref_field, double* int_field);
 int mfb_export_matrix(mfb_ctx* ctx, const double* Kint, double* Kref_dev);
 int mfb_export_pattern(mfb_ctx* ctx, int* K_I, int* K_J, int* K_J_ptr, int* K_val_ids);  // device ptrs (nullable)
+
+// mfb_dist.cu
+int mfb_node_ids_init(mfb_ctx* ctx, const unsigned char* owned_ref_dev, const long long* gid_ref_dev);
+int mfb_halo_add(mfb_ctx* ctx, double* v, int nv);
+int mfb_allreduce_sum(mfb_ctx* ctx, double* dev, int n);
+bool mfb_is_distributed(mfb_ctx* ctx);
+void mfb_comm_free(mfb_ctx* ctx);
 
 // mfb_krylov.cu
 int mfb_spmv_internal(mfb_ctx* ctx, const double* K, const double* x, double* y);

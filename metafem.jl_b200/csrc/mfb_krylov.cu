@@ -157,23 +157,30 @@ __global__ void __launch_bounds__(256) k_spmv_bsr_flat(const int* __restrict__ n
     }
 }
 
-// jac[node][v] = |K[diag(node)][v][v]|, 1 when the (v,v) block is not populated (Jacobi_By_Diagonal)
+// jac[node][v] = K[diag(node)][v][v] (partial on interface nodes; completed by the halo sum, then k_jacobi_abs),
+// 1 when the (v,v) block is not populated (Jacobi_By_Diagonal leaves the initial 1.0)
 __global__ void k_jacobi_diag(const int* nodeptr, const int* nodecol, const double* K, const int* diag_ok, int64_t N,
-                              int nv, double* jac) {
+                              int nv, const unsigned char* owned, double* jac) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= N * nv) return;
     int64_t a = t / nv;
     int v = (int)(t % nv);
-    double j = 1.0;
+    double j = (owned == nullptr || owned[a]) ? 1.0 : 0.0;   // the default 1.0 must be counted once across ranks
     if (diag_ok[v]) {
+        j = 0.0;
         int lo = nodeptr[a], hi = nodeptr[a + 1] - 1;
         while (lo < hi) {
             int mid = (lo + hi) >> 1;
             if (nodecol[mid] < a) lo = mid + 1; else hi = mid;
         }
-        if (nodecol[lo] == a) j = fabs(K[(size_t)lo * nv * nv + v * nv + v]);
+        if (nodecol[lo] == a) j = K[(size_t)lo * nv * nv + v * nv + v];
     }
     jac[t] = j;
+}
+
+__global__ void k_jacobi_abs(double* jac, int64_t n) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) jac[t] = fabs(jac[t]);
 }
 
 // Ks[ent][i][k] = K[ent][i][k] / jac[col][k]   (gather-copy of 02_Preconditioner.jl:35 fused with Mat_Div_Jacobi)
@@ -196,7 +203,7 @@ struct LinComb {
 };
 
 // optional fused squared norm of the result (partials[block]); 4 independent elements per thread for memory-level parallelism
-__global__ void __launch_bounds__(TPB) k_lincomb(LinComb L, int64_t n, double* partial_norm2) {
+__global__ void __launch_bounds__(TPB) k_lincomb(LinComb L, int64_t n, double* partial_norm2, const unsigned char* owned, int nv) {
     double nrm = 0.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
@@ -219,7 +226,7 @@ __global__ void __launch_bounds__(TPB) k_lincomb(LinComb L, int64_t n, double* p
         for (int u = 0; u < 4; ++u)
             if (idx[u] >= 0) {
                 L.y[idx[u]] = sv[u];
-                nrm += sv[u] * sv[u];
+                if (owned == nullptr || owned[idx[u] / nv]) nrm += sv[u] * sv[u];
             }
     }
     if (partial_norm2) {
@@ -264,7 +271,7 @@ struct MultiDot {
     const double* y[MAXD];
 };
 // partials[k][block] = sum over the block's grid-stride slice of x_k*y_k (warp-shuffle + smem reduction)
-__global__ void __launch_bounds__(TPB) k_multidot(MultiDot M, int64_t n, double* partials) {
+__global__ void __launch_bounds__(TPB) k_multidot(MultiDot M, int64_t n, double* partials, const unsigned char* owned, int nv) {
     __shared__ double sh[TPB / 32];
     for (int k0 = 0; k0 < M.n; k0 += 4) {
         double acc[4] = {0, 0, 0, 0};
@@ -273,12 +280,14 @@ __global__ void __launch_bounds__(TPB) k_multidot(MultiDot M, int64_t n, double*
         for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
             const int64_t i1 = i + stride;
             const bool ok1 = i1 < n;
+            const double w0 = (owned == nullptr || owned[i / nv]) ? 1.0 : 0.0;        // count every node once (its owner)
+            const double w1 = (ok1 && (owned == nullptr || owned[i1 / nv])) ? 1.0 : 0.0;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 if (k < nk) {
                     const double a0 = M.x[k0 + k][i], b0 = M.y[k0 + k][i];
                     const double a1 = ok1 ? M.x[k0 + k][i1] : 0.0, b1 = ok1 ? M.y[k0 + k][i1] : 0.0;
-                    acc[k] += a0 * b0 + a1 * b1;
+                    acc[k] += w0 * (a0 * b0) + w1 * (a1 * b1);
                 }
         }
 #pragma unroll
@@ -321,9 +330,11 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
     return z ^ (z >> 31);
 }
 // FEM_rand: uniform [0,1) (reference uses unseeded cuRAND, 04_GPU_Utils.jl:22); counter-based and seeded here
-__global__ void k_rand(double* p, int64_t n, unsigned long long seed, unsigned long long stream_id) {
+// keyed by the GLOBAL reference node id, so the vector does not depend on the internal numbering or on the partition
+__global__ void k_rand(double* p, int64_t n, unsigned long long seed, unsigned long long stream_id, const long long* gid, int nv) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        unsigned long long h = splitmix64(splitmix64(seed ^ (stream_id * 0xD1B54A32D192ED03ull)) + (unsigned long long)i);
+        const unsigned long long g = (unsigned long long)gid[i / nv] * nv + (unsigned long long)(i % nv);
+        unsigned long long h = splitmix64(splitmix64(seed ^ (stream_id * 0xD1B54A32D192ED03ull)) + g);
         p[i] = (double)(h >> 11) * (1.0 / 9007199254740992.0);
     }
 }
@@ -369,9 +380,11 @@ struct Solver {
     const double* A;
     int spmv = 0;
 
+    const unsigned char* mask() const { return mfb_is_distributed(ctx) ? ctx->owned.p : nullptr; }
     int mul(double* y, const double* x) {
         spmv++;
-        return mfb_spmv_internal(ctx, A, x, y);
+        MFB_TRY(mfb_spmv_internal(ctx, A, x, y));
+        return mfb_halo_add(ctx, y, ctx->n_var);          // complete the interface rows (no-op on one GPU)
     }
     // dots: results in ctx->h_scal[0..k)
     int dots(int k, const double* const* xs, const double* const* ys) {
@@ -379,8 +392,9 @@ struct Solver {
         M.n = k;
         for (int i = 0; i < k; ++i) { M.x[i] = xs[i]; M.y[i] = ys[i]; }
         double* partials = ctx->scal.p + 64;
-        LAUNCH(k_multidot, RED_BLOCKS, TPB, M, n, partials);
+        LAUNCH(k_multidot, RED_BLOCKS, TPB, M, n, partials, mask(), ctx->n_var);
         LAUNCH(k_reduce_partials, k, 256, partials, RED_BLOCKS, ctx->scal.p);
+        MFB_TRY(mfb_allreduce_sum(ctx, ctx->scal.p, k));
         MFB_CUDA(cudaMemcpyAsync(ctx->h_scal, ctx->scal.p, k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         MFB_CUDA(cudaStreamSynchronize(ctx->stream));
         return MFB_OK;
@@ -398,9 +412,10 @@ struct Solver {
         L.y = y; L.ay = ay; L.n = k;
         for (int i = 0; i < k; ++i) { L.c[i] = c[i]; L.x[i] = xs[i]; }
         double* partials = norm2 ? ctx->scal.p + 64 : nullptr;
-        LAUNCH(k_lincomb, RED_BLOCKS, TPB, L, n, partials);
+        LAUNCH(k_lincomb, RED_BLOCKS, TPB, L, n, partials, mask(), ctx->n_var);
         if (norm2) {
             LAUNCH(k_reduce_partials, 1, 256, partials, RED_BLOCKS, ctx->scal.p);
+            MFB_TRY(mfb_allreduce_sum(ctx, ctx->scal.p, 1));
             MFB_CUDA(cudaMemcpyAsync(ctx->h_scal, ctx->scal.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
             MFB_CUDA(cudaStreamSynchronize(ctx->stream));
             *norm2 = ctx->h_scal[0];
@@ -414,7 +429,8 @@ struct Solver {
         LAUNCH(k_axpby_batch, RED_BLOCKS, TPB, Bt, n);
         return MFB_OK;
     }
-    double nn(double norm2) const { return std::sqrt(norm2) / std::sqrt((double)n); }  // normalized_norm
+    double n_global = 0.0;   // global number of DOFs (sum of owned nodes over ranks)
+    double nn(double norm2) const { return std::sqrt(norm2) / std::sqrt(n_global > 0 ? n_global : (double)n); }  // normalized_norm
 };
 
 // r = b - A x, returns normalized norm
@@ -442,7 +458,7 @@ int idrs(Solver& S, double* x, const double* b, double* r, double tol, int maxit
     double** G = &W[2 * s];
     double* Ar = W[3 * s];
     for (int k = 0; k < s; ++k) {
-        LAUNCH(k_rand, RED_BLOCKS, TPB, P[k], n, (unsigned long long)seed, (unsigned long long)(pass * 64 + k));
+        LAUNCH(k_rand, RED_BLOCKS, TPB, P[k], n, (unsigned long long)seed, (unsigned long long)(pass * 64 + k), ctx->gid.p, ctx->n_var);
         MFB_CUDA(cudaMemsetAsync(U[k], 0, n * sizeof(double), ctx->stream));
         MFB_CUDA(cudaMemsetAsync(G[k], 0, n * sizeof(double), ctx->stream));
     }
@@ -536,7 +552,7 @@ int bicgstabl_gs(Solver& S, double* x, const double* b, double* r, double tol, i
     for (int i = 1; i <= s; ++i) R[i] = W[i - 1];
     for (int i = 0; i <= s; ++i) U[i] = W[s + i];
     double* r_shadow = W[2 * s + 1];
-    LAUNCH(k_rand, RED_BLOCKS, TPB, r_shadow, n, (unsigned long long)seed, (unsigned long long)(pass * 64 + 63));
+    LAUNCH(k_rand, RED_BLOCKS, TPB, r_shadow, n, (unsigned long long)seed, (unsigned long long)(pass * 64 + 63), ctx->gid.p, ctx->n_var);
     for (int i = 1; i <= s; ++i) MFB_CUDA(cudaMemsetAsync(R[i], 0, n * sizeof(double), ctx->stream));
     for (int i = 0; i <= s; ++i) MFB_CUDA(cudaMemsetAsync(U[i], 0, n * sizeof(double), ctx->stream));
     std::vector<double> gam(s, 0.0), gamp(s, 0.0), gampp(s, 0.0), sig(s, 0.0), tau(s * s, 0.0);
@@ -652,7 +668,10 @@ extern "C" int mfb_krylov_solve(mfb_ctx* ctx, int method, int s, int maxiter, in
         DevBuf<int> d_ok;
         MFB_CUDA(d_ok.alloc(nv));
         MFB_CUDA(cudaMemcpyAsync(d_ok.p, diag_ok.data(), nv * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        LAUNCH(k_jacobi_diag, nblk(n), TPB, ctx->nodeptr.p, ctx->nodecol.p, ctx->K_total.p, d_ok.p, ctx->N, nv, ctx->jac.p);
+        LAUNCH(k_jacobi_diag, nblk(n), TPB, ctx->nodeptr.p, ctx->nodecol.p, ctx->K_total.p, d_ok.p, ctx->N, nv,
+               mfb_is_distributed(ctx) ? ctx->owned.p : (const unsigned char*)nullptr, ctx->jac.p);
+        MFB_TRY(mfb_halo_add(ctx, ctx->jac.p, nv));
+        LAUNCH(k_jacobi_abs, nblk(n), TPB, ctx->jac.p, n);
         LAUNCH(k_scale_copy, nblk(nval), TPB, ctx->nodecol.p, ctx->K_total.p, ctx->jac.p, nval, nv, Ks.p);
         MFB_CUDA(cudaStreamSynchronize(ctx->stream));
         d_ok.release();
@@ -665,6 +684,7 @@ extern "C" int mfb_krylov_solve(mfb_ctx* ctx, int method, int s, int maxiter, in
     MFB_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), ctx->stream));
     MFB_CUDA(cudaMemcpyAsync(r, b, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     Solver S{ctx, n, Ks.p};
+    S.n_global = ctx->n_global_nodes * nv;
     mfb_solve_info inf;
     memset(&inf, 0, sizeof(inf));
     {
@@ -800,6 +820,7 @@ extern "C" int mfb_residue_norm(mfb_ctx* ctx, double* out) {
     MFB_REQUIRE(ctx->residue.p, MFB_ERR_STATE, "vectors not allocated (call mfb_pattern_build)");
     MFB_TRY(ensure_scalars(ctx));
     Solver S{ctx, ctx->N * ctx->n_var, nullptr};
+    S.n_global = ctx->n_global_nodes * ctx->n_var;
     double d;
     MFB_TRY(S.dot1(ctx->residue.p, ctx->residue.p, &d));
     *out = S.nn(d);

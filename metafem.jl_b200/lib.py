@@ -66,6 +66,9 @@ _SIGS = {
     "mfb_update_dx": (C.c_int, [_P, _P, C.c_int, C.c_double]),
     "mfb_commit_step": (C.c_int, [_P]),
     "mfb_residue_norm": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "mfb_comm_unique_id": (C.c_int, [_P]),
+    "mfb_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "mfb_interface_set": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
 }
 
 _lib = None
