@@ -30,8 +30,8 @@ def parse():
     p.add_argument("--steps", type=int, default=3)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--n", type=int, default=88, help="elements per box side (88 -> 8.39M DOF)")
-    p.add_argument("--cpu-n", type=int, default=20, help="elements per side of the bounded CPU-baseline sample")
+    p.add_argument("--box", dest="n", type=int, default=88, help="elements per box side (88 -> 8.39M DOF)")
+    p.add_argument("--cpu-box", dest="cpu_n", type=int, default=20, help="elements per side of the bounded CPU-baseline sample")
     p.add_argument("--numbering", default="scattered", choices=["scattered", "sorted"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--ncu", action="store_true", help="profiler capture run: exactly W warm-up steps, no e2e pass; "
@@ -164,7 +164,7 @@ def run_reference(args):
     cb["value"] = v
     print(json.dumps({"impl": "reference", "metric": "newton_step_dof_per_s", "value": v, "unit": "DOF/s",
                       "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True,
-                      "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                       "config": workload_config(args, sample_n=args.cpu_n), "cpu_baseline": cb,
                       "e2e": {"value": v, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -198,16 +198,36 @@ def main():
     torch.cuda.set_device(local)
     K, W = args.steps, max(args.warmup, 0)
 
-    # ---- setup (untimed): mesh tables, pattern, kernels ---------------------------------------------------------
-    # replicas-only multi-GPU in this round: every rank runs the same box (weak scaling, no data-path collective)
+    # ---- setup (untimed): mesh tables, partition, pattern, kernels -------------------------------------------------
+    # N > 1: STRONG scaling of the same box -- element blocks (slabs) per rank, interface exchange-add + allreduce over NCCL
     t_setup = time.perf_counter()
     n = args.n
-    tables = fmesh.box_tables((1.0, 1.0, 1.0), (n, n, n), "CUBE", groups=("left", "right"), numbering=args.numbering)
+    gtables = fmesh.box_tables((1.0, 1.0, 1.0), (n, n, n), "CUBE", groups=("left", "right"), numbering=args.numbering)
     spec = wf.neo_hookean(fixed_bg=1, traction_bg=2)
+    ndof_global = 3 * gtables.variable_size
+    gstate = initial_state(gtables.x, 1.0 / n)
+    if world > 1:
+        from metafem_jl_b200.frontend import partition as pt
+        sub = pt.make_subdomains(gtables, pt.split_elements(gtables, world), ranks=[rank])[rank]
+        tables = sub.tables
+        gstate = [pt.scatter_field(sub, v) for v in gstate]
+    else:
+        sub, tables = None, gtables
+    n_el_global = gtables.controlpoint_IDs.shape[1]
+    del gtables
     fd = m.FEM_Domain(tables, spec, device=local)
     stream = torch.cuda.Stream()
     fd.ctx.call("mfb_set_stream", L.ptr(stream.cuda_stream))
-    for b, v in zip(("d1", "d2", "d3"), initial_state(tables.x, 1.0 / n)):
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(m.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        torch.cuda.synchronize()
+        dist.barrier()            # torch's own communicator is fully up before the library creates its own
+        with torch.cuda.stream(stream):
+            m.init_distributed(fd, sub, rank, world, bytes(idt.cpu().numpy().tobytes()))
+    for b, v in zip(("d1", "d2", "d3"), gstate):
         fd.controlpoints[b][:] = v
     fd.controlpoints["Pl1"][:] = LOAD
     fd.global_vars.update(mu=MU, lam=LAM, tau_b=1000 * max(MU, LAM))
@@ -282,26 +302,27 @@ def main():
     if rank != 0:
         return
     ms_step = ms_total / K
-    value = world * ndof / (ms_step * 1e-3)
-    e2e_val = world * ndof / (ms_e2e / K * 1e-3)
+    value = ndof_global / (ms_step * 1e-3)
+    e2e_val = ndof_global / (ms_e2e / K * 1e-3)
     peak, peak_kind = hbm_peak()
     spmv_ms = pms[0] / max(pcnt[0], 1)
     spmv_bytes = 12.0 * nnz + 4.0 * (ndof + 1) + 16.0 * ndof
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
     asm_ms = pms[1] / max(pcnt[1], 1)
     elem_ms = pms[4] / max(pcnt[4], 1)
-    n_el = n ** 3
+    n_el = tables.controlpoint_IDs.shape[1]
     asm_bytes = 8.0 * nnz + 8.0 * ndof + 8.0 * ndof + 24.0 * tables.variable_size + 4.0 * 20 * n_el + 4.0 * 400 * n_el
     out = {
         "metric": "newton_step_dof_per_s", "value": value, "unit": "DOF/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": workload_config(args, extra={
-            "dof": ndof, "nnz": nnz, "elements": n_el, "parallelism": "replicas only" if world > 1 else "single GPU",
+            "dof": ndof_global, "dof_rank0": ndof, "nnz_rank0": nnz, "elements": n_el_global,
+            "parallelism": f"element blocks (x slabs) over {world} GPUs, NCCL interface exchange-add + allreduce" if world > 1 else "single GPU",
             "krylov_iterations_per_step": info.iterations, "spmv_per_step": info.spmv_count, "passes": info.passes,
             "solver_converged": bool(info.converged), "initial_residual": res.value, "final_residual": info.residual,
             "setup_s": t_setup}),
-        "newton_step_ms": ms_step, "assembly_ms": asm_ms, "assembly_dof_per_s": ndof / (asm_ms * 1e-3),
+        "newton_step_ms": ms_step, "assembly_ms": asm_ms, "assembly_dof_per_s": ndof_global / (asm_ms * 1e-3),
         "element_kernel_ms": elem_ms, "solve_ms": pms[3] / max(pcnt[3], 1), "spmv_ms": spmv_ms,
         "spmv_share_of_step": pms[0] / ms_total,
         "roofline": {"bound": "hbm", "kernel": "k_spmv_bsr<3>", "achieved": achieved, "peak": peak, "unit": "GB/s",
