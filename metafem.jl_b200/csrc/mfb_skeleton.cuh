@@ -80,29 +80,40 @@ __device__ __forceinline__ double inv3(const double (&J)[3][3], double (&I)[3][3
 
 // Form contract (emitted code):
 //   static constexpr int NV, NA, NQ, L1 (= max_time_level + 1), BOUNDARY (0/1), LINEAR (0/1),
-//                        NW (inner words), NCW (cp words), NC (cp fields), NT (K terms), HAS_RES, HAS_K, TPB;
+//                        NW (inner words), NCW (cp words), NC (cp fields), HAS_RES, HAS_K, TPB,
+//                        NSD (dual slots used by K terms), KS (base slots used), ND (= NV*NSD*NV*KS dense tangent entries),
+//                        MT, NTC (register tile of the tangent contraction: MT rows x NTC columns per thread);
+//   __device__ static constexpr int dslot(int i), bslot(int i);        // slot ids (0:N, 1..3: d/dx) of the used dual/base slots
 //   template <class S> __device__ static void words(const S& s, int q, double* w, double* c);
 //        // w[k] = interpolation of inner word k, c[k] = of CONTROLPOINT_VAR word k  (_Var_Basic)
 //   __device__ static void point(const double* w, const double* c, const double* nrm, const MfbArgs& A,
-//                                double* R /*[NV*4], zeroed*/, double* D /*[NT]*/);   // NOT yet weighted
-//   __device__ static void kacc(double* acc /*[NV*NV]*/, const double* Ga /*[4]*/, const double* Gb /*[4]*/,
-//                               const double* Dq /*[NT]*/);
+//                                double* R /*[NV*4], zeroed*/, double* D /*[ND], zeroed*/);   // NOT yet weighted
+//        // D[((dp*NSD + dsi)*NV + bp)*KS + ksi] = d(residual integrand of dual (dp, dslot(dsi)))/d(word (bp, bslot(ksi))) * K_params[td]
 //
 // One thread block works on one item at a time (grid-stride over items); TPB threads.
-// Shared memory per item: G[NQ][NA][4] (physical shape values/gradients), Dq[NQ][NT], Rq[NQ][NV*4],
-// node data xe[NA][3], ue[L1][NA][NV], ce[NC][NA], node ids.
+//   phase A  gather node data of the element into shared memory
+//   phase B  one thread per quadrature point: Jacobian, inverse, w*detJ (or facet normal and w*|t1 x t2|), physical
+//            gradients G[q][slot][a], interpolation of every word, emitted point function -> R[q][.], D[q][.] (weighted)
+//   phase C1 residual: r[a][v] = sum_q sum_slot G[q][slot][a] R[q][v][slot]                       (_Res_Basic)
+//   phase C2 tangent, sum-factorised per quadrature point (replaces one _Kval_Basic launch per term):
+//            stage 1  T[ks][(a,dp,bp)] = sum_dsi G[q][dslot(dsi)][a] * D[q][dp][dsi][bp][ks]       (NA*NV threads)
+//            stage 2  K[(a,dp,bp)][b] += sum_ks T[ks][(a,dp,bp)] * G[q][bslot(ks)][b]             (MT x NTC register tiles,
+//                     operands read from shared memory with 128-bit loads: 2 MT + NTC/2 wavefronts per MT*NTC DFMA)
+//            then red.global.add.f64 of the element matrix into the block-CSR values.
 template <int NA>
-__device__ __forceinline__ double interp(const double* G4 /*stride 4*/, const double* u, int ustride) {
+__device__ __forceinline__ double interp(const double* Ga /*[NA] contiguous*/, const double* u, int ustride) {
     double s = 0.0;
 #pragma unroll 4
-    for (int a = 0; a < NA; ++a) s += G4[4 * a] * u[a * ustride];
+    for (int a = 0; a < NA; ++a) s += Ga[a] * u[a * ustride];
     return s;
 }
 
 template <class F>
 struct Smem {
-    double G[F::NQ][F::NA][4];
-    double D[F::NQ][F::NT > 0 ? F::NT : 1];
+    static constexpr int MROWS = F::NA * F::NV * F::NV;
+    double G[F::NQ][4][F::NA];                     // first two members stay 16 B aligned (even element counts)
+    double T[2][F::KS > 0 ? F::KS : 1][MROWS];
+    double D[F::NQ][F::ND > 0 ? F::ND : 1];
     double R[F::NQ][F::NV * 4];
     double xe[F::NA][3];
     double ue[F::L1][F::NA][F::NV];
@@ -115,7 +126,7 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<F>& S = *reinterpret_cast<Smem<F>*>(smem_raw);
     const int tid = threadIdx.x;
-    constexpr int NA = F::NA, NQ = F::NQ, NV = F::NV;
+    constexpr int NA = F::NA, NQ = F::NQ, NV = F::NV, BB = NV * NV, MROWS = NA * NV * NV;
 
     for (long long item = blockIdx.x; item < A.n_items; item += gridDim.x) {
         long long e = item;
@@ -181,51 +192,109 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
             }
             for (int a = 0; a < NA; ++a) {
                 double d0 = ref[(1 * NQ + q) * NA + a], d1 = ref[(2 * NQ + q) * NA + a], d2 = ref[(3 * NQ + q) * NA + a];
-                S.G[q][a][0] = ref[(0 * NQ + q) * NA + a];
+                S.G[q][0][a] = ref[(0 * NQ + q) * NA + a];
 #pragma unroll
-                for (int s = 0; s < 3; ++s) S.G[q][a][1 + s] = (d0 * I[0][s] + d1 * I[1][s]) + d2 * I[2][s];
+                for (int s = 0; s < 3; ++s) S.G[q][1 + s][a] = (d0 * I[0][s] + d1 * I[1][s]) + d2 * I[2][s];
             }
             double w[F::NW > 0 ? F::NW : 1], c[F::NCW > 0 ? F::NCW : 1];
             F::words(S, q, w, c);
-            double R[NV * 4], D[F::NT > 0 ? F::NT : 1];
+            double R[NV * 4], D[F::ND > 0 ? F::ND : 1];
 #pragma unroll
             for (int k = 0; k < NV * 4; ++k) R[k] = 0.0;
+#pragma unroll
+            for (int k = 0; k < F::ND; ++k) D[k] = 0.0;
             F::point(w, c, nrm, A, R, D);
 #pragma unroll
             for (int k = 0; k < NV * 4; ++k) S.R[q][k] = R[k] * wgt;
 #pragma unroll
-            for (int k = 0; k < F::NT; ++k) S.D[q][k] = D[k] * wgt;
+            for (int k = 0; k < F::ND; ++k) S.D[q][k] = D[k] * wgt;
         }
         __syncthreads();
         // ---- phase C1: residual ------------------------------------------------------------
-        if (F::HAS_RES) {
+        if constexpr (F::HAS_RES) {
             for (int i = tid; i < NA * NV; i += F::TPB) {
                 int v = i % NV, a = i / NV;
                 double s = 0.0;
                 for (int q = 0; q < NQ; ++q) {
 #pragma unroll
-                    for (int sl = 0; sl < 4; ++sl) s += S.G[q][a][sl] * S.R[q][v * 4 + sl];
+                    for (int sl = 0; sl < 4; ++sl) s += S.G[q][sl][a] * S.R[q][v * 4 + sl];
                 }
                 if (s != 0.0) red_add(A.res + (size_t)S.node[a] * NV + v, s);
             }
         }
-        // ---- phase C2: tangent, one (a,b) node pair per thread -----------------------------
-        if (F::HAS_K) {
-            for (int p = tid; p < NA * NA; p += F::TPB) {
-                int a = p / NA, b = p % NA;
-                double acc[NV * NV];
+        // ---- phase C2: tangent ---------------------------------------------------------------
+        if constexpr (F::HAS_K) {
+            constexpr int MT = F::MT, NTC = F::NTC, KS = F::KS, NSD = F::NSD;
+            constexpr int NRG = (MROWS + MT - 1) / MT, NCG = (NA + NTC - 1) / NTC;
+            static_assert(NRG * NCG <= F::TPB, "tangent tiling needs more threads than the block has");
+            static_assert(MT % 2 == 0 && NTC % 2 == 0 && NA % 2 == 0 && MROWS % 2 == 0, "128-bit shared-memory loads need even tiles");
+            const int rg = tid % NRG, cg = tid / NRG;
+            const int m0 = rg * MT, b0 = cg * NTC;
+            const bool tile_on = tid < NRG * NCG;
+            double acc[MT][NTC];
 #pragma unroll
-                for (int k = 0; k < NV * NV; ++k) acc[k] = 0.0;
-                for (int q = 0; q < NQ; ++q) {
-                    double Ga[4], Gb[4];
+            for (int r = 0; r < MT; ++r)
 #pragma unroll
-                    for (int sl = 0; sl < 4; ++sl) { Ga[sl] = S.G[q][a][sl]; Gb[sl] = S.G[q][b][sl]; }
-                    F::kacc(acc, Ga, Gb, S.D[q]);
+                for (int c = 0; c < NTC; ++c) acc[r][c] = 0.0;
+            for (int q = 0; q < NQ; ++q) {
+                const int buf = q & 1;
+                // stage 1: thread (a, dp) fills T[ks][(a,dp,bp)] for all bp, ks
+                for (int i = tid; i < NA * NV; i += F::TPB) {
+                    const int a = i / NV, dp = i - a * NV;
+                    double g[NSD > 0 ? NSD : 1];
+#pragma unroll
+                    for (int d = 0; d < NSD; ++d) g[d] = S.G[q][F::dslot(d)][a];
+                    const double* Dq = &S.D[q][dp * NSD * NV * KS];
+#pragma unroll
+                    for (int bp = 0; bp < NV; ++bp)
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) {
+                            double t = 0.0;
+#pragma unroll
+                            for (int d = 0; d < NSD; ++d) t += g[d] * Dq[(d * NV + bp) * KS + ks];
+                            S.T[buf][ks][(a * NV + dp) * NV + bp] = t;
+                        }
                 }
-                double* dst = A.Kval + (size_t)A.emap[e * (NA * NA) + p] * (NV * NV);
+                __syncthreads();   // T[buf] complete; T[buf^1] (read in the previous iteration) may now be overwritten next time
+                if (tile_on) {
 #pragma unroll
-                for (int k = 0; k < NV * NV; ++k)
-                    if (acc[k] != 0.0) red_add(dst + k, acc[k]);
+                    for (int ks = 0; ks < KS; ++ks) {
+                        double ta[MT], gb[NTC];
+                        const double2* tp = reinterpret_cast<const double2*>(&S.T[buf][ks][m0]);
+                        const double2* gp = reinterpret_cast<const double2*>(&S.G[q][F::bslot(ks)][b0]);
+#pragma unroll
+                        for (int r = 0; r < MT / 2; ++r) {
+                            const bool ok = m0 + 2 * r < MROWS;
+                            double2 v = ok ? tp[r] : make_double2(0.0, 0.0);
+                            ta[2 * r] = v.x; ta[2 * r + 1] = v.y;
+                        }
+#pragma unroll
+                        for (int c = 0; c < NTC / 2; ++c) {
+                            const bool ok = b0 + 2 * c < NA;
+                            double2 v = ok ? gp[c] : make_double2(0.0, 0.0);
+                            gb[2 * c] = v.x; gb[2 * c + 1] = v.y;
+                        }
+#pragma unroll
+                        for (int r = 0; r < MT; ++r)
+#pragma unroll
+                            for (int c = 0; c < NTC; ++c) acc[r][c] += ta[r] * gb[c];
+                    }
+                }
+            }
+            if (tile_on) {
+#pragma unroll
+                for (int r = 0; r < MT; ++r) {
+                    const int m = m0 + r;
+                    if (m >= MROWS) break;
+                    const int a = m / BB, rem = m - a * BB;
+                    const int* em = A.emap + e * (NA * NA) + a * NA + b0;
+#pragma unroll
+                    for (int c = 0; c < NTC; ++c) {
+                        if (b0 + c >= NA) break;
+                        const double v = acc[r][c];
+                        if (v != 0.0) red_add(A.Kval + (size_t)em[c] * BB + rem, v);
+                    }
+                }
             }
         }
     }

@@ -243,3 +243,33 @@ def neo_hookean(fixed_bg=1, traction_bg=3):
         # non-symmetric second-order tensor naming: 1 + (i-1) + 3 (j-1)  (03_Word.jl:66)
         f.add(f"d{i}", (), sum(P.cpvar(f"Pl{1 + (i - 1) + 3 * (j - 1)}") * P.n(j) for j in (1, 2, 3)))
     return P.spec()
+
+
+def thermo_elasticity(E=210e3, nu=0.0, tau_b=None, rho=1e3, c=0.01, h=100.0, C=1000.0, k=100.0, alpha=0.05e-3,
+                      L_box=1.0, fixed_bg=1, thermal_bg=3):
+    """examples/thermal_elasticity/themal_hypo_elasticity.jl:45-71: fields T, d with first time derivatives
+    (max_time_level = 1). No leading minus in this script's forms (only consistency matters)."""
+    lam, mu = E * nu / ((1 + nu) * (1 - 2 * nu)), E / (2 * (1 + nu))
+    tau_b = 1000 * E / L_box if tau_b is None else tau_b
+    P = Physics(3)
+    T = P.u("T")
+    gd = [[P.u(f"d{i}", 0, (j,)) for j in (1, 2, 3)] for i in (1, 2, 3)]
+    eps = [[(gd[i][j] + gd[j][i]) / 2 - (alpha * T if i == j else 0) for j in range(3)] for i in range(3)]
+    tr = eps[0][0] + eps[1][1] + eps[2][2]
+    sig = [[lam * (1 if i == j else 0) * tr + 2 * mu * eps[i][j] for j in range(3)] for i in range(3)]
+    dom = P.form("domain")
+    dom.add("T", (), C * P.u("T", 1))                                   # C (T, T_t)
+    for i in (1, 2, 3):
+        dom.add("T", (i,), k * P.u("T", 0, (i,)))                       # k (T_i, T_i)
+    # (eps_ij, sigma_ij): the variation of eps_ij = sym grad d - alpha T delta_ij gives a d_a;b test term and a T test term
+    for a in range(3):
+        for b in range(3):
+            dom.add(f"d{a+1}", (b + 1,), (sig[a][b] + sig[b][a]) / 2)
+    dom.add("T", (), -alpha * (sig[0][0] + sig[1][1] + sig[2][2]))
+    for i in (1, 2, 3):
+        dom.add(f"d{i}", (), rho * c * P.u(f"d{i}", 1))                 # (d_i, rho c d_i,t)
+    f = P.form("boundary", fixed_bg)
+    for i in (1, 2, 3):
+        f.add(f"d{i}", (), tau_b * P.u(f"d{i}"))
+    P.form("boundary", thermal_bg).add("T", (), h * (T - P.cpvar("Te")))
+    return P.spec()

@@ -49,6 +49,8 @@ def spec_for(name):
         return wf.linear_elasticity(lam, mu, 1000.0 * E, fixed_bg=1, traction_bgs=((2, "sl"),))
     if name == "neo_hookean":
         return wf.neo_hookean(fixed_bg=1, traction_bg=2)
+    if name == "thermo_elasticity":
+        return wf.thermo_elasticity(fixed_bg=1, thermal_bg=3)
     raise KeyError(name)
 
 
@@ -62,6 +64,9 @@ def build_case(name, n=(3, 2, 2), size=(1.5, 1.0, 1.0), seed=0):
     spec = spec_for(name)
     if name == "thermal":
         bgs = [faces["all"]]
+    elif name == "thermo_elasticity":
+        bgs = [faces["left"], np.concatenate([faces["bottom"], faces["top"], faces["right"]]),
+               np.concatenate([faces["front"], faces["back"]])]
     else:
         bgs = [faces["left"], faces["right"]]
     mesh = fm.mesh_Classical(m, bgs, shape)
@@ -73,6 +78,15 @@ def build_case(name, n=(3, 2, 2), size=(1.5, 1.0, 1.0), seed=0):
         dom.cp["T"][:] = 293.15 + 5.0 * np.sin(mesh.x[0]) + rng.uniform(-1e-3, 1e-3, N)
         dom.cp["s"][:] = 1600.0 + 10 * mesh.x[1]
         dom.globalfield.converge_tol = 1e-8
+    elif name == "thermo_elasticity":
+        dom.cp["T"][:] = 20.0 * np.cos(mesh.x[1]) + rng.uniform(-1e-3, 1e-3, N)
+        dom.cp["T_t1"][:] = 0.3 * mesh.x[0]
+        dom.cp["Te"][:] = 300.0 * (mesh.x[1] < 1e-9)
+        for i, b in enumerate(("d1", "d2", "d3")):
+            dom.cp[b][:] = 1e-3 * np.sin(1.3 * mesh.x[(i + 1) % 3] + 0.2 * i) * mesh.x[0]
+            dom.cp[b + "_t1"][:] = 1e-4 * mesh.x[(i + 2) % 3]
+        dom.globalfield.dt = 1.0
+        dom.globalfield.converge_tol = 1e-6
     else:
         for i, b in enumerate(("d1", "d2", "d3")):
             dom.cp[b][:] = 0.02 * np.sin(1.3 * mesh.x[(i + 1) % 3] + 0.2 * i) * mesh.x[0] + rng.uniform(-1e-3, 1e-3, N) * h

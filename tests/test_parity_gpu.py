@@ -8,7 +8,7 @@ from oracle import assembly as oasm, solver as osv
 pytestmark = pytest.mark.gpu
 
 CASES = [("thermal", (3, 2, 2)), ("linear_elasticity", (3, 2, 2)), ("neo_hookean", (3, 2, 2)),
-         ("neo_hookean", (5, 4, 3)), ("thermal", (4, 4, 3))]
+         ("neo_hookean", (5, 4, 3)), ("thermal", (4, 4, 3)), ("thermo_elasticity", (3, 2, 2))]
 
 
 @pytest.fixture(scope="module", params=CASES, ids=lambda c: f"{c[0]}-{'x'.join(map(str, c[1]))}")
