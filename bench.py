@@ -34,6 +34,8 @@ def parse():
     p.add_argument("--cpu-box", dest="cpu_n", type=int, default=20, help="elements per side of the bounded CPU-baseline sample")
     p.add_argument("--numbering", default="scattered", choices=["scattered", "sorted"])
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--assembly-only", action="store_true", help="development aid: skip the Krylov solve in every step "
+                                                                "(prints timings of the assembly only; never a bench value)")
     p.add_argument("--ncu", action="store_true", help="profiler capture run: exactly W warm-up steps, no e2e pass; "
                                                       "numbers printed by such a run are never bench values")
     return p.parse_args()
@@ -256,6 +258,8 @@ def main():
         fd.ctx.call("mfb_update_x_star", L.ptr(alpha), len(alpha))
         fd.ctx.call("mfb_assemble_nonlinear", L.ptr(kp), len(kp), gf.t, gf.dt)
         fd.ctx.call("mfb_residue_norm", C.byref(res))
+        if args.assembly_only:
+            return
         fd.ctx.call("mfb_krylov_solve", L.MFB_BICGSTABL_GS, SOLVER["s"], SOLVER["maxiter"], SOLVER["max_pass"], TOL, 1234,
                     None, C.byref(info))
         fd.ctx.call("mfb_update_dx", L.ptr(beta), len(beta), -1.0)
@@ -300,6 +304,10 @@ def main():
     ms_e2e = timed(True, K) if not args.ncu else ms_total
     clk = clocks.stop()
     if rank != 0:
+        return
+    if args.assembly_only:
+        print(json.dumps({"assembly_only": True, "assembly_ms": pms[1] / max(pcnt[1], 1), "element_kernel_ms": pms[4] / max(pcnt[4], 1),
+                          "boundary_kernels_ms": pms[7] / max(pcnt[7], 1), "clocks": clk}))
         return
     ms_step = ms_total / K
     value = ndof_global / (ms_step * 1e-3)

@@ -38,7 +38,20 @@ enum {
 };
 
 /* Krylov methods: Sv_func! of iterative_Solve! (02_Preconditioner.jl:32) */
-enum { MFB_IDRS = 0 /* idrs!, 04_IDRs.jl:26-95 */, MFB_BICGSTABL_GS = 1 /* bicgstabl_GS!, 03_BiCGstabl.jl:18-96 */ };
+enum {
+    MFB_IDRS = 0,         /* idrs!,         04_IDRs.jl:26-95 */
+    MFB_BICGSTABL_GS = 1, /* bicgstabl_GS!, 03_BiCGstabl.jl:18-96 */
+    MFB_BICGSTABL = 2,    /* bicgstabl!,    03_BiCGstabl.jl:98-162 (MR part by LU of the Gram matrix) */
+    MFB_GMRES = 3,        /* gmres!,        05_GMRES.jl:46-101 (restart length s) */
+    MFB_CGS = 4,          /* cgs!,          07_CGS.jl:10-50 */
+    MFB_CGS2 = 5,         /* cgs2!,         07_CGS.jl:52-105 */
+    MFB_TFQMR = 6,        /* tfqmr!,        08_QMR.jl:3-76 */
+    MFB_LSQR = 7          /* lsqr!,         06_LSQR.jl:10-73 (needs A' x: transposed block SpMV) */
+};
+/* Pr_func! / Pl_func of iterative_Solve! (02_Preconditioner.jl:78-177) */
+enum { MFB_PR_JACOBI = 0 /* Pr_Jacobi! by diagonal (default) */, MFB_PR_JACOBI_COLUMN = 1 /* normalized_by_column = true */,
+       MFB_PR_IDENTITY = 2 };
+enum { MFB_PL_IDENTITY = 0 /* default */, MFB_PL_JACOBI = 1 /* Pl_Jacobi by diagonal */, MFB_PL_JACOBI_ROW = 2 /* normalized_by_row */ };
 
 /* vectors of GlobalField (src/solver/01_Types.jl:110-132) */
 enum { MFB_VEC_X = 0, MFB_VEC_DX = 1, MFB_VEC_X_STAR = 2, MFB_VEC_RESIDUE = 3 };
@@ -135,6 +148,12 @@ typedef struct {
     int32_t threads_per_block;    /* launch shape chosen by the emitter */
     int32_t smem_bytes;           /* dynamic shared memory per block */
     int32_t has_nonlinear_K;      /* 1 if the nonlinear kernel adds K terms */
+    /* quadrature-point callbacks (INTEGRATION_POINT_VAR words, symbolics/08_Tensor.jl:175-183): */
+    const char *eval_kernel;      /* entry point filling the callback's argument arrays, or NULL */
+    int32_t n_qp_in;              /* integration-point arrays the nonlinear kernel reads (callback outputs) */
+    const char *const *qp_in_names;
+    int32_t n_qp_out;             /* integration-point arrays the eval kernel writes (callback arguments) */
+    const char *const *qp_out_names;
 } mfb_block_desc;
 int mfb_kernel_compile(mfb_ctx *ctx, const char *cuda_src, int n_blocks, const mfb_block_desc *blocks);
 /* Compile-only check of an emitted translation unit (needs no device): writes the NVRTC log (or the
@@ -148,6 +167,35 @@ int mfb_assemble_linear(mfb_ctx *ctx, const double *K_params, int n_params);
 /* K_nonlinear_func: residue .= 0; K_total .= K_linear; residual + nonlinear gradient terms,
  * evaluated at the context's x_star (05_CodeGenerator.jl:278-288). t and dt are the GLOBAL_VARs :t/:dt. */
 int mfb_assemble_nonlinear(mfb_ctx *ctx, const double *K_params, int n_params, double t, double dt);
+
+/* ---- integration-point variables and the quadrature-point callback ------------------------
+ * The J2 example defines `ep{i,j} = strain_updater(e{1,1}, ..., e{3,3})`
+ * (examples/hypo_elastic_plasticity/J2Plasticity.jl:55): the generated updater evaluates the six arguments on whole
+ * [n_q, n_el] device arrays, calls Main.strain_updater on them and reads the six outputs as external words
+ * (symbolics/08_Tensor.jl:175-183,210). Here the nonlinear update is two-phase:
+ *   mfb_eval_qp_args      fills the argument arrays (named "<func>_arg<k>");
+ *   the caller runs its callback on the arrays (device pointers from mfb_qp_array, e.g. wrapped as CuArrays,
+ *   or the built-in J2 return map below) and leaves the outputs in the arrays named like the output words;
+ *   mfb_assemble_nonlinear reads them.
+ * Arrays are library-owned, [n_q, n_el] column-major (q fastest) in the reference's element order, zero on creation. */
+int mfb_qp_array(mfb_ctx *ctx, const char *name, double **device_ptr, int64_t *n);
+int mfb_qp_set(mfb_ctx *ctx, const char *name, const double *values, int64_t n);
+int mfb_qp_get(mfb_ctx *ctx, const char *name, double *values, int64_t n);
+int mfb_eval_qp_args(mfb_ctx *ctx, double t, double dt);
+
+/* Built-in return map = the example's MaterialState callable, iterate_stress! and update_States!
+ * (J2Plasticity.jl:76-198) as ONE element-wise kernel over all quadrature points. State arrays
+ * "<prefix>.ep1..6", "<prefix>.b1..6", "<prefix>.Y" (committed) and "<prefix>.b_eval1..6", "<prefix>.Y_eval"
+ * are integration-point arrays of the context; ep_eval is written to the arrays named ep_names (Voigt order).
+ *   e_names  [6]  argument arrays in the callback's order e11, e12, e13, e22, e23, e33
+ *   ep_names [6]  output arrays in Voigt order 11, 22, 33, 23, 13, 12 (symbolics/03_Word.jl:37) */
+typedef struct {
+    double lambda, mu, Eb, Ep, f_res;
+} mfb_j2_params;
+int mfb_j2_init(mfb_ctx *ctx, const char *prefix, double Y_initial, const char *const *e_names,
+                const char *const *ep_names);
+int mfb_j2_iterate_stress(mfb_ctx *ctx, const char *prefix, const mfb_j2_params *params, int64_t *n_yielded);
+int mfb_j2_update_states(mfb_ctx *ctx, const char *prefix);
 
 /* ---- linear algebra ---------------------------------------------------------------------
  * y = K * x in reference numbering (mul!, src/misc/04_GPU_Utils.jl:131). */
@@ -167,6 +215,13 @@ typedef struct {
  * (may be NULL: result stays in the context for mfb_update_dx). */
 int mfb_krylov_solve(mfb_ctx *ctx, int method, int s, int maxiter, int max_pass, double tol,
                      uint64_t seed, double *delta_out, mfb_solve_info *info);
+
+/* Same with the preconditioner choices of iterative_Solve!: Pr_func! in {Pr_Jacobi!, Pr_Jacobi!(normalized_by_column),
+ * Identity}, Pl_func in {Identity, Pl_Jacobi, Pl_Jacobi(normalized_by_row)}; with a left preconditioner the per-pass
+ * tolerance is rescaled by min(||Pl r|| / ||r||, 1) (:50-53). checkiter: residual check period of tfqmr!.
+ * Pl_ILU (cuSPARSE ilu02!, :179-194) is not provided. */
+int mfb_krylov_solve_ex(mfb_ctx *ctx, int method, int s, int maxiter, int max_pass, double tol, uint64_t seed,
+                        int pr_mode, int pl_mode, int checkiter, double *delta_out, mfb_solve_info *info);
 
 /* ---- time stepping (src/solver/04_Time_Domain.jl) ----------------------------------------
  * Device-resident versions of initialize_dx! (:20-30), update_x_star! (:41-49),

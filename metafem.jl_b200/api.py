@@ -93,6 +93,7 @@ class FEM_Domain:
         self.K_nonlinear_func = None
         self.linear_solver = None
         self.last_solve = None
+        self.callbacks = {}          # quadrature-point callbacks by function name (Main.<func> in the reference)
         N = tables.variable_size
         # controlpoints.<sym> tables (host copies, like cpts.T / cpts.d1 in the example scripts)
         self.controlpoints = {}
@@ -146,8 +147,73 @@ class FEM_Domain:
         for g in self.spec["globals"]:
             self.ctx.call("mfb_global_set", g.encode(), float(self.global_vars[g]))
 
+    # -- INTEGRATION_POINT_VAR arrays [n_q, n_el] (reference element order) ------------------------------------
+    @property
+    def qp_shape(self):
+        return (self.tables.controlpoint_IDs.shape[1], self.tables.ref_itp_vals.shape[0])      # C order of [n_q, n_el]
+
+    def qp_get(self, name):
+        out = np.empty(self.qp_shape)
+        self.ctx.call("mfb_qp_get", name.encode(), L.ptr(out), out.size)
+        return out
+
+    def qp_set(self, name, values):
+        v = _f64(np.broadcast_to(values, self.qp_shape))
+        self.ctx.call("mfb_qp_set", name.encode(), L.ptr(v), v.size)
+
+    def qp_device_ptr(self, name):
+        """Device address of a library-owned integration-point array (what a Julia callback wraps with unsafe_wrap)."""
+        p, n = C.c_void_p(), C.c_int64(0)
+        self.ctx.call("mfb_qp_array", name.encode(), C.byref(p), C.byref(n))
+        return p.value, n.value
+
     def close(self):
         self.ctx.close()
+
+
+class HostCallback:
+    """Generic quadrature-point callback running on the HOST: pulls the argument arrays, calls ``fn(*args)`` (numpy
+    arrays shaped [n_el, n_q]) and pushes the returned arrays. The device-side equivalent in Julia wraps the pointers
+    from mfb_qp_array as CuArrays (INTEGRATION.md)."""
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __call__(self, fem_domain, call):
+        outs = self.fn(*[fem_domain.qp_get(n) for n in call["arg_names"]])
+        for n, v in zip(call["outs"], outs):
+            fem_domain.qp_set(n, v)
+
+
+class J2MaterialState:
+    """MaterialState of examples/hypo_elastic_plasticity/J2Plasticity.jl:76-198 on the library's built-in return map:
+    calling it is ``strain_updater(e1_1, ..., e3_3)`` (iterate_stress!), ``update_States`` commits ep, b, Y."""
+
+    def __init__(self, fem_domain, Y_initial, lam, mu, Eb, Ep, f_res, prefix="j2", func="strain_updater"):
+        self.dom, self.prefix, self.Y_initial = fem_domain, prefix, float(Y_initial)
+        self.lam, self.mu, self.Eb, self.Ep, self.f_res = lam, mu, Eb, Ep, f_res
+        self.n_yielded = 0
+        call = next(c for b in fem_domain.spec["blocks"] for c in b.get("qp_calls", []) if c["func"] == func)
+        self._e = (C.c_char_p * 6)(*[n.encode() for n in call["arg_names"]])
+        self._ep = (C.c_char_p * 6)(*[n.encode() for n in call["outs"]])
+        self.reset()
+
+    def reset(self):
+        """ep .= 0; b .= 0; Y .= Y_initial (J2Plasticity.jl:256-262)."""
+        self.dom.ctx.call("mfb_j2_init", self.prefix.encode(), self.Y_initial, self._e, self._ep)
+
+    def __call__(self, fem_domain=None, call=None):
+        prm = L.J2Params(self.lam, self.mu, self.Eb, self.Ep, self.f_res)
+        n = C.c_int64(0)
+        self.dom.ctx.call("mfb_j2_iterate_stress", self.prefix.encode(), C.byref(prm), C.byref(n))
+        self.n_yielded = n.value
+
+    def update_States(self):
+        self.dom.ctx.call("mfb_j2_update_states", self.prefix.encode())
+
+    def state(self, what):
+        """Committed state arrays [n_el, n_q]: what in ep1..6, b1..6, Y."""
+        return self.dom.qp_get(f"{self.prefix}.{what}")
 
 
 def comm_unique_id():
@@ -233,6 +299,12 @@ def compile_Updater_GPU(domain_ID, fem_domain, tpb=128):
         arr[i].n_globals, arr[i].global_names = len(d["global_names"]), gls
         arr[i].threads_per_block, arr[i].smem_bytes = d["threads_per_block"], d["smem_bytes"]
         arr[i].has_nonlinear_K = d["has_nonlinear_K"]
+        qin = (C.c_char_p * max(len(d["qp_in_names"]), 1))(*[s.encode() for s in d["qp_in_names"]])
+        qout = (C.c_char_p * max(len(d["qp_out_names"]), 1))(*[s.encode() for s in d["qp_out_names"]])
+        keep += [qin, qout]
+        arr[i].eval_kernel = d["eval_kernel"].encode() if d["eval_kernel"] else None
+        arr[i].n_qp_in, arr[i].qp_in_names = len(d["qp_in_names"]), qin
+        arr[i].n_qp_out, arr[i].qp_out_names = len(d["qp_out_names"]), qout
     dom.ctx.call("mfb_kernel_compile", src.encode(), len(descs), arr)
 
     def update_K_Linear(time_discretization, fem_domain=dom):
@@ -244,6 +316,14 @@ def compile_Updater_GPU(domain_ID, fem_domain, tpb=128):
         kp = _f64(time_discretization.K_params)
         gf = fem_domain.globalfield
         fem_domain.sync_fields()
+        calls = [c for b in fem_domain.spec["blocks"] for c in b.get("qp_calls", [])]
+        if calls:
+            # two-phase update: argument arrays -> Main.<func> on whole arrays -> residual (08_Tensor.jl:175-183,210)
+            fem_domain.ctx.call("mfb_eval_qp_args", gf.t, gf.dt)
+            for c in calls:
+                if c["func"] not in fem_domain.callbacks:
+                    raise KeyError(f"quadrature-point callback {c['func']!r} is not defined (fem_domain.callbacks)")
+                fem_domain.callbacks[c["func"]](fem_domain, c)
         fem_domain.ctx.call("mfb_assemble_nonlinear", L.ptr(kp), len(kp), gf.t, gf.dt)
 
     dom.K_linear_func, dom.K_nonlinear_func = update_K_Linear, update_K_NonLinear
@@ -288,18 +368,29 @@ def update_OneStep(time_discretization, max_iter=4, fem_domain=None, log=None):
     return history
 
 
-_METHODS = {"idrs": L.MFB_IDRS, "idrs!": L.MFB_IDRS, "bicgstabl_GS": L.MFB_BICGSTABL_GS, "bicgstabl_GS!": L.MFB_BICGSTABL_GS}
+_METHODS = {"idrs": L.MFB_IDRS, "bicgstabl_GS": L.MFB_BICGSTABL_GS, "bicgstabl": L.MFB_BICGSTABL, "gmres": L.MFB_GMRES,
+            "cgs": L.MFB_CGS, "cgs2": L.MFB_CGS2, "tfqmr": L.MFB_TFQMR, "lsqr": L.MFB_LSQR}
+_PR = {"Pr_Jacobi": L.PR_JACOBI, "Pr_Jacobi_column": L.PR_JACOBI_COLUMN, "Identity": L.PR_IDENTITY}
+_PL = {"Identity": L.PL_IDENTITY, "Pl_Jacobi": L.PL_JACOBI, "Pl_Jacobi_row": L.PL_JACOBI_ROW}
 
 
-def iterative_Solve(fem_domain, Sv_func="idrs", max_pass=4, maxiter=2000, s=4, seed=1234, want_delta=False, log=None):
-    """iterative_Solve!(globalfield; Sv_func!, max_pass, maxiter, s) (02_Preconditioner.jl:32-76), right-Jacobi."""
-    if Sv_func not in _METHODS:
-        raise ValueError(f"Sv_func {Sv_func!r} is not on the B200 hot path (supported: idrs, bicgstabl_GS)")
+def iterative_Solve(fem_domain, Sv_func="idrs", Pr_func="Pr_Jacobi", Pl_func="Identity", max_pass=4, maxiter=2000, s=4,
+                    seed=1234, checkiter=200, want_delta=False, log=None):
+    """iterative_Solve!(globalfield; Sv_func!, Pr_func!, Pl_func, max_pass, maxiter, s) (02_Preconditioner.jl:32-76).
+    Sv_func: idrs, bicgstabl_GS, bicgstabl, gmres, cgs, cgs2, tfqmr, lsqr (a trailing "!" is accepted);
+    Pr_func: Pr_Jacobi (default) | Pr_Jacobi_column (normalized_by_column = true) | Identity;
+    Pl_func: Identity (default) | Pl_Jacobi | Pl_Jacobi_row (normalized_by_row = true). Pl_ILU is not provided."""
+    name = Sv_func.rstrip("!")
+    if name not in _METHODS:
+        raise ValueError(f"Sv_func {Sv_func!r} is not provided (supported: {', '.join(_METHODS)})")
+    if Pr_func not in _PR or Pl_func not in _PL:
+        raise ValueError(f"unsupported preconditioner {Pr_func!r} / {Pl_func!r}")
     dom, gf = fem_domain, fem_domain.globalfield
     info = L.SolveInfo()
     delta = np.empty(gf.basicfield_size) if want_delta else None
-    rc = dom.ctx.call("mfb_krylov_solve", _METHODS[Sv_func], int(s), int(maxiter), int(max_pass),
-                      float(gf.converge_tol), int(seed), L.ptr(delta), C.byref(info))
+    rc = dom.ctx.call("mfb_krylov_solve_ex", _METHODS[name], int(s), int(maxiter), int(max_pass),
+                      float(gf.converge_tol), int(seed), _PR[Pr_func], _PL[Pl_func], int(checkiter), L.ptr(delta),
+                      C.byref(info))
     dom.last_solve = dict(passes=info.passes, iterations=info.iterations, spmv=info.spmv_count,
                           converged=bool(info.converged), residual=info.residual,
                           initial_residual=info.initial_residual)

@@ -54,8 +54,8 @@ struct DevBuf {
 
 struct BlockKernels {
     int kind = 0, bg_ID = 0;
-    cudaKernel_t lin = nullptr, nonlin = nullptr;
-    std::vector<std::string> cp_vars, globals;
+    cudaKernel_t lin = nullptr, nonlin = nullptr, eval = nullptr;
+    std::vector<std::string> cp_vars, globals, qp_in, qp_out;
     int tpb = 128, smem = 0, has_nonlinear_K = 0;
 };
 
@@ -112,6 +112,10 @@ struct mfb_ctx {
     bool have_delta = false;
     std::map<std::string, DevBuf<double>> fields;  // internal order [N]
     std::map<std::string, double> globals;
+    std::map<std::string, DevBuf<double>> qp;      // INTEGRATION_POINT_VAR arrays [n_q, n_el], reference element order
+    struct J2State { std::string e[6], ep[6]; };
+    std::map<std::string, J2State> j2;
+    DevBuf<unsigned long long> qp_counter;         // yielded-point counter of the J2 return map
 
     // ---- kernels ----
     cudaLibrary_t lib = nullptr;
@@ -178,5 +182,9 @@ int mfb_allreduce_sum(mfb_ctx* ctx, double* dev, int n);
 bool mfb_is_distributed(mfb_ctx* ctx);
 void mfb_comm_free(mfb_ctx* ctx);
 
+// mfb_qp.cu
+int mfb_qp_lookup(mfb_ctx* ctx, const std::string& name, double** p);   // creates the array (zeroed) on first use
+
 // mfb_krylov.cu
 int mfb_spmv_internal(mfb_ctx* ctx, const double* K, const double* x, double* y);
+int mfb_spmv_t_internal(mfb_ctx* ctx, const double* K, const double* x, double* y);   // y = K' x

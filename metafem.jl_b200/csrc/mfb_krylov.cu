@@ -11,8 +11,10 @@
 // node-major interleaved [node][NV]. Every vector update of a Krylov step is one fused launch
 // (k_lincomb / k_axpby_batch) and every group of reductions is one fused multi-dot launch; scalars
 // come back through one pinned 8*k byte copy per group instead of one blocking cuBLAS call each.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <initializer_list>
 
 #include "mfb_internal.h"
 
@@ -181,6 +183,59 @@ __global__ void k_jacobi_diag(const int* nodeptr, const int* nodecol, const doub
 __global__ void k_jacobi_abs(double* jac, int64_t n) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t < n) jac[t] = fabs(jac[t]);
+}
+
+// y[col][k] += sum_i K[ent][i][k] * x[row][i]  -- transposed block SpMV for lsqr! (tmul!, 06_LSQR.jl:25,42); y zeroed by the
+// caller. One warp per block row, lane <-> fixed (i,k) like the forward kernel; the NV partial products of one output
+// component sit NV lanes apart and are folded with shuffles before ONE red.global.add per (entry, k).
+template <int NV>
+__global__ void __launch_bounds__(256) k_spmv_bsr_t(const int* __restrict__ nodeptr, const int* __restrict__ nodecol,
+                                                    const double* __restrict__ K, const double* __restrict__ x,
+                                                    double* __restrict__ y, int64_t N) {
+    constexpr int B = NV * NV, EPW = 32 / B, ACTIVE = EPW * B;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (row >= N) return;
+    const int le = lane / B, ik = lane - le * B, i = ik / NV, k = ik - i * NV;
+    const bool on = lane < ACTIVE;
+    const double xi = on ? x[(size_t)row * NV + i] : 0.0;
+    const int s = nodeptr[row], t = nodeptr[row + 1];
+    for (int e0 = s; e0 < t; e0 += EPW) {
+        const int e = e0 + le;
+        const bool live = on && e < t;
+        double v = live ? K[(size_t)e * B + ik] * xi : 0.0;
+        // fold over i: lanes ik = i*NV + k, i = 0..NV-1 -> lane with i == 0 collects
+#pragma unroll
+        for (int j = 1; j < NV; ++j) {
+            const double o = __shfl_down_sync(0xffffffffu, v, j * NV);
+            if (i == 0) v += o;
+        }
+        if (live && i == 0) atomicAdd(y + (size_t)nodecol[e] * NV + k, v);
+    }
+}
+
+// jac[col][k] += K[ent][i][k]^2 (Jacobi2_By_Colomn, 02_Preconditioner.jl:122-129) / jac[row][i] += K^2 (Jacobi_By_Row :169-176)
+__global__ void k_jacobi_sq(const int* nodeptr, const int* nodecol, const double* K, int64_t N, int nv, int by_row, double* jac) {
+    const int B = nv * nv;
+    const int64_t row = blockIdx.x;
+    for (int e = nodeptr[row]; e < nodeptr[row + 1]; ++e)
+        for (int t = threadIdx.x; t < B; t += blockDim.x) {
+            const double v = K[(size_t)e * B + t];
+            const int i = t / nv, k = t - i * nv;
+            atomicAdd(by_row ? jac + (size_t)row * nv + i : jac + (size_t)nodecol[e] * nv + k, v * v);
+        }
+}
+__global__ void k_sqrt(double* v, int64_t n) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) v[t] = sqrt(v[t]);
+}
+__global__ void k_fill1(double* v, int64_t n) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) v[t] = 1.0;
+}
+__global__ void k_div_inplace(double* y, const double* d, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) y[i] /= d[i];
 }
 
 // Ks[ent][i][k] = K[ent][i][k] / jac[col][k]   (gather-copy of 02_Preconditioner.jl:35 fused with Mat_Div_Jacobi)
@@ -354,6 +409,23 @@ __global__ void k_div(double* y, const double* x, const double* d, int64_t n) {
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
+int mfb_spmv_t_internal(mfb_ctx* ctx, const double* K, const double* x, double* y) {
+    const int64_t N = ctx->N;
+    const unsigned grid = (unsigned)((N * 32 + 255) / 256);
+    MFB_CUDA(cudaMemsetAsync(y, 0, N * ctx->n_var * sizeof(double), ctx->stream));
+    ProfScope ps(ctx, MFB_T_SPMV);
+    switch (ctx->n_var) {
+        case 1: LAUNCH(k_spmv_bsr_t<1>, grid, 256, ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N); break;
+        case 2: LAUNCH(k_spmv_bsr_t<2>, grid, 256, ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N); break;
+        case 3: LAUNCH(k_spmv_bsr_t<3>, grid, 256, ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N); break;
+        case 4: LAUNCH(k_spmv_bsr_t<4>, grid, 256, ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N); break;
+        case 5: LAUNCH(k_spmv_bsr_t<5>, grid, 256, ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N); break;
+        default: ctx->err = "n_var > 5 not supported by the transposed block SpMV"; return MFB_ERR_ARG;
+    }
+    MFB_CUDA(cudaGetLastError());
+    return MFB_OK;
+}
+
 int mfb_spmv_internal(mfb_ctx* ctx, const double* K, const double* x, double* y) {
     const int64_t N = ctx->N;
     unsigned grid = (unsigned)((N + SPMV_ROWS - 1) / SPMV_ROWS);
@@ -380,11 +452,26 @@ struct Solver {
     const double* A;
     int spmv = 0;
 
+    const double* pl = nullptr;   // Pl_Jacobi vector (left preconditioner: b ./= jac_vec after every product), or null
+
     const unsigned char* mask() const { return mfb_is_distributed(ctx) ? ctx->owned.p : nullptr; }
+    int Pl(double* v) {
+        if (pl) LAUNCH(k_div_inplace, nblk(n), TPB, v, pl, n);
+        return MFB_OK;
+    }
+    // y = Pl(A x): every mul! of the reference's solvers is followed by Pl(.)
     int mul(double* y, const double* x) {
         spmv++;
         MFB_TRY(mfb_spmv_internal(ctx, A, x, y));
-        return mfb_halo_add(ctx, y, ctx->n_var);          // complete the interface rows (no-op on one GPU)
+        MFB_TRY(mfb_halo_add(ctx, y, ctx->n_var));        // complete the interface rows (no-op on one GPU)
+        return Pl(y);
+    }
+    // y = Pl(A' x)  (tmul!, used by lsqr!)
+    int tmul(double* y, const double* x) {
+        spmv++;
+        MFB_TRY(mfb_spmv_t_internal(ctx, A, x, y));
+        MFB_TRY(mfb_halo_add(ctx, y, ctx->n_var));
+        return Pl(y);
     }
     // dots: results in ctx->h_scal[0..k)
     int dots(int k, const double* const* xs, const double* const* ys) {
@@ -433,13 +520,28 @@ struct Solver {
     double nn(double norm2) const { return std::sqrt(norm2) / std::sqrt(n_global > 0 ? n_global : (double)n); }  // normalized_norm
 };
 
-// r = b - A x, returns normalized norm
-int true_residual(Solver& S, double* r, const double* b, const double* x, double* res) {
-    MFB_TRY(S.mul(r, x));
+// r = Pl(b - A x) (the opening lines of every solver) or, with left == false, the plain b - A x of iterative_Solve!;
+// returns the normalized norm
+int true_residual(Solver& S, double* r, const double* b, const double* x, double* res, bool left = true) {
+    mfb_ctx* ctx = S.ctx;
+    const double* keep = S.pl;
+    S.pl = nullptr;
+    int rc = S.mul(r, x);
+    S.pl = keep;
+    MFB_TRY(rc);
     double c[1] = {1.0};
     const double* xs[1] = {b};
     double n2;
-    MFB_TRY(S.lincomb(r, -1.0, 1, c, xs, &n2));
+    if (left && S.pl) {
+        MFB_TRY(S.lincomb(r, -1.0, 1, c, xs));
+        MFB_TRY(S.Pl(r));
+        double d;
+        MFB_TRY(S.dot1(r, r, &d));
+        n2 = d;
+    } else {
+        MFB_TRY(S.lincomb(r, -1.0, 1, c, xs, &n2));
+    }
+    (void)ctx;
     *res = S.nn(n2);
     return MFB_OK;
 }
@@ -640,42 +742,447 @@ int ensure_work(mfb_ctx* ctx, int count, int64_t n) {
     return MFB_OK;
 }
 
+
+// small helpers for the remaining methods -----------------------------------------------------------------------------
+struct Vec {
+    Solver& S;
+    int set(double* y, std::initializer_list<double> c, std::initializer_list<const double*> x, double* norm2 = nullptr) {
+        return S.lincomb(y, 0.0, (int)c.size(), c.begin(), x.begin(), norm2);                 // y = sum c_i x_i
+    }
+    int add(double* y, std::initializer_list<double> c, std::initializer_list<const double*> x, double* norm2 = nullptr) {
+        return S.lincomb(y, 1.0, (int)c.size(), c.begin(), x.begin(), norm2);                 // y += sum c_i x_i
+    }
+    int dot(const double* x, const double* y, double* out) { return S.dot1(x, y, out); }
+};
+
+// bicgstabl!  (03_BiCGstabl.jl:98-162): BiCG part as in bicgstabl_GS!, MR part by the normal equations M gamma = M[:,1]
+// solved with a (host) LU, as the reference does with lu!.
+int bicgstabl_lu(Solver& S, double* x, const double* b, double* r, double tol, int maxiter, int s, uint64_t seed, int pass,
+                 std::vector<double*>& W, int* iters) {
+    mfb_ctx* ctx = S.ctx;
+    const int64_t n = S.n;
+    Vec V{S};
+    double res;
+    MFB_TRY(true_residual(S, r, b, x, &res));
+    // the reference tests the UN-normalised norm here (`r_norm <= tol`, :103-104)
+    if (res * std::sqrt(S.n_global > 0 ? S.n_global : (double)n) <= tol) { *iters = 0; return MFB_OK; }
+    int iter = 1;
+    std::vector<double*> R(s + 1), U(s + 1);
+    R[0] = r;
+    for (int i = 1; i <= s; ++i) R[i] = W[i - 1];
+    for (int i = 0; i <= s; ++i) U[i] = W[s + i];
+    double* r_shadow = W[2 * s + 1];
+    LAUNCH(k_rand, RED_BLOCKS, TPB, r_shadow, n, (unsigned long long)seed, (unsigned long long)(pass * 64 + 63), ctx->gid.p, ctx->n_var);
+    for (int i = 1; i <= s; ++i) MFB_CUDA(cudaMemsetAsync(R[i], 0, n * sizeof(double), ctx->stream));
+    for (int i = 0; i <= s; ++i) MFB_CUDA(cudaMemsetAsync(U[i], 0, n * sizeof(double), ctx->stream));
+    std::vector<double> gam(s), M((s + 1) * (s + 1));
+    double omega = 1.0, rho0 = 1.0, alpha = 0.0;
+    std::vector<double*> yy(s + 1);
+    std::vector<double> aa(s + 1), bb(s + 1);
+    std::vector<const double*> xx(2 * s + 2), ys(2 * s + 2);
+    std::vector<double> cf(2 * s + 2);
+    while (true) {
+        rho0 *= -omega;
+        for (int j = 0; j < s; ++j) {
+            double rho1;
+            MFB_TRY(V.dot(r_shadow, R[j], &rho1));
+            const double beta = alpha * rho1 / rho0;
+            rho0 = rho1;
+            for (int i = 0; i <= j; ++i) { yy[i] = U[i]; aa[i] = -beta; bb[i] = 1.0; xx[i] = R[i]; }
+            MFB_TRY(S.axpby_batch(j + 1, yy.data(), aa.data(), bb.data(), xx.data()));      // U[i] = R[i] - beta U[i]
+            MFB_TRY(S.mul(U[j + 1], U[j]));
+            double d;
+            MFB_TRY(V.dot(r_shadow, U[j + 1], &d));
+            alpha = rho0 / d;
+            for (int i = 0; i <= j; ++i) { yy[i] = R[i]; aa[i] = 1.0; bb[i] = -alpha; xx[i] = U[i + 1]; }
+            MFB_TRY(S.axpby_batch(j + 1, yy.data(), aa.data(), bb.data(), xx.data()));      // R[i] -= alpha U[i+1]
+            MFB_TRY(S.mul(R[j + 1], R[j]));
+            MFB_TRY(V.add(x, {alpha}, {U[0]}));
+        }
+        // MR part: Gram matrix of R[0..s] in fused multi-dot launches
+        int nd = 0;
+        std::vector<const double*> da, db;
+        for (int j = 0; j <= s; ++j)
+            for (int i = 0; i <= j; ++i) { da.push_back(R[i]); db.push_back(R[j]); }
+        std::vector<double> g(da.size());
+        for (size_t o = 0; o < da.size(); o += MAXD) {
+            const int k = (int)std::min<size_t>(MAXD, da.size() - o);
+            MFB_TRY(S.dots(k, da.data() + o, db.data() + o));
+            for (int i = 0; i < k; ++i) g[o + i] = ctx->h_scal[i];
+        }
+        for (int j = 0; j <= s; ++j)
+            for (int i = 0; i <= j; ++i) { M[i * (s + 1) + j] = M[j * (s + 1) + i] = g[nd++]; }
+        // gamma = M[L,L] \ M[L,1], L = 2..s+1: Gaussian elimination with partial pivoting (lu!)
+        {
+            std::vector<double> Am(s * s), rhs(s);
+            for (int i = 0; i < s; ++i) {
+                rhs[i] = M[(i + 1) * (s + 1)];
+                for (int j = 0; j < s; ++j) Am[i * s + j] = M[(i + 1) * (s + 1) + j + 1];
+            }
+            for (int c = 0; c < s; ++c) {
+                int pv = c;
+                for (int i = c + 1; i < s; ++i) if (std::fabs(Am[i * s + c]) > std::fabs(Am[pv * s + c])) pv = i;
+                if (pv != c) { for (int j = 0; j < s; ++j) std::swap(Am[c * s + j], Am[pv * s + j]); std::swap(rhs[c], rhs[pv]); }
+                for (int i = c + 1; i < s; ++i) {
+                    const double f = Am[i * s + c] / Am[c * s + c];
+                    for (int j = c; j < s; ++j) Am[i * s + j] -= f * Am[c * s + j];
+                    rhs[i] -= f * rhs[c];
+                }
+            }
+            for (int i = s - 1; i >= 0; --i) {
+                double v = rhs[i];
+                for (int j = i + 1; j < s; ++j) v -= Am[i * s + j] * gam[j];
+                gam[i] = v / Am[i * s + i];
+            }
+        }
+        int nt = 0;
+        for (int i = 0; i < s; ++i) { cf[nt] = -gam[i]; xx[nt++] = U[i + 1]; }
+        MFB_TRY(S.lincomb(U[0], 1.0, nt, cf.data(), xx.data()));
+        nt = 0;
+        for (int i = 0; i < s; ++i) { cf[nt] = gam[i]; xx[nt++] = R[i]; }
+        MFB_TRY(S.lincomb(x, 1.0, nt, cf.data(), xx.data()));
+        nt = 0;
+        for (int i = 0; i < s; ++i) { cf[nt] = -gam[i]; xx[nt++] = R[i + 1]; }
+        double n2;
+        MFB_TRY(S.lincomb(R[0], 1.0, nt, cf.data(), xx.data(), &n2));
+        omega = gam[s - 1];
+        iter += s;
+        if (S.nn(n2) <= tol || iter >= maxiter) { *iters = iter; return MFB_OK; }
+    }
+}
+
+// Hessenberg least squares by Givens rotations (05_GMRES.jl:7-37): H is (w+1) x w column-major with leading dimension ld
+void hessenberg_solve(std::vector<double>& H, int ld, int w, std::vector<double>& rhs) {
+    for (int i = 0; i < w; ++i) {
+        const double f = H[i * ld + i], g = H[i * ld + i + 1];
+        double c, sn;
+        if (g == 0.0) { c = 1.0; sn = 0.0; }
+        else if (f == 0.0) { c = 0.0; sn = 1.0; }
+        else { const double rr = std::copysign(std::hypot(f, g), f); c = f / rr; sn = g / rr; }
+        H[i * ld + i] = c * f + sn * g;
+        for (int j = i + 1; j < w; ++j) {
+            const double tmp = -sn * H[j * ld + i] + c * H[j * ld + i + 1];
+            H[j * ld + i] = c * H[j * ld + i] + sn * H[j * ld + i + 1];
+            H[j * ld + i + 1] = tmp;
+        }
+        const double tmp = -sn * rhs[i] + c * rhs[i + 1];
+        rhs[i] = c * rhs[i] + sn * rhs[i + 1];
+        rhs[i + 1] = tmp;
+    }
+    for (int i = w - 1; i >= 0; --i) {
+        double v = rhs[i];
+        for (int j = i + 1; j < w; ++j) v -= H[j * ld + i] * rhs[j];
+        rhs[i] = v / H[i * ld + i];
+    }
+}
+
+// gmres!  (05_GMRES.jl:46-101): restarted every s iterations, modified Gram-Schmidt. Vectors: Q[0..s].
+int gmres(Solver& S, double* x, const double* b, double* r, double tol, int maxiter, int s, std::vector<double*>& W, int* iters) {
+    Vec V{S};
+    double res;
+    MFB_TRY(true_residual(S, r, b, x, &res));
+    if (res <= tol) { *iters = 0; return MFB_OK; }
+    int iter = 1;
+    std::vector<double*> Q(s + 1);
+    for (int i = 0; i <= s; ++i) Q[i] = W[i];
+    const int ld = s + 1;
+    std::vector<double> H((size_t)ld * s, 0.0), y(s + 1, 0.0);
+    double d;
+    MFB_TRY(V.dot(r, r, &d));
+    double r_norm = std::sqrt(d);
+    y[0] = r_norm;
+    std::vector<double> cf(s + 1);
+    std::vector<const double*> xs(s + 1);
+    while (true) {
+        MFB_TRY(V.set(Q[0], {1.0 / r_norm}, {r}));
+        for (int i = 1; i <= s; ++i) {
+            MFB_TRY(S.mul(Q[i], Q[i - 1]));
+            for (int j = 0; j < i; ++j) {
+                double h;
+                MFB_TRY(V.dot(Q[j], Q[i], &h));
+                H[(i - 1) * ld + j] = h;
+                MFB_TRY(V.add(Q[i], {-h}, {Q[j]}));
+            }
+            double n2;
+            MFB_TRY(V.dot(Q[i], Q[i], &n2));
+            const double hn = std::sqrt(n2);
+            H[(i - 1) * ld + i] = hn;
+            if (hn == 0.0) {   // exact solve inside the cycle (:72-79)
+                const int w = i - 1;
+                if (w > 0) {
+                    hessenberg_solve(H, ld, w, y);
+                    for (int j = 0; j < w; ++j) { cf[j] = y[j]; xs[j] = Q[j]; }
+                    MFB_TRY(S.lincomb(x, 1.0, w, cf.data(), xs.data()));
+                }
+                *iters = iter + i - 1;
+                return MFB_OK;
+            }
+            MFB_TRY(V.set(Q[i], {1.0 / hn}, {Q[i]}));
+        }
+        hessenberg_solve(H, ld, s, y);
+        for (int j = 0; j < s; ++j) { cf[j] = y[j]; xs[j] = Q[j]; }
+        MFB_TRY(S.lincomb(x, 1.0, s, cf.data(), xs.data()));
+        iter += s;
+        MFB_TRY(true_residual(S, r, b, x, &res));
+        if (res <= tol || iter > maxiter) { *iters = iter; return MFB_OK; }
+        std::fill(y.begin(), y.end(), 0.0);
+        std::fill(H.begin(), H.end(), 0.0);
+        MFB_TRY(V.dot(r, r, &d));
+        r_norm = std::sqrt(d);
+        y[0] = r_norm;
+    }
+}
+
+// cgs!  (07_CGS.jl:10-50). Vectors: r0, u, p, s, v. (The reference's FEM_buffer work vectors are uninitialised; zero here.)
+int cgs(Solver& S, double* x, const double* b, double* r, double tol, int maxiter, std::vector<double*>& W, int* iters) {
+    mfb_ctx* ctx = S.ctx;
+    const int64_t n = S.n;
+    Vec V{S};
+    double res;
+    MFB_TRY(true_residual(S, r, b, x, &res));
+    if (res <= tol) { *iters = 0; return MFB_OK; }
+    int iter = 1;
+    double *r0 = W[0], *u = W[1], *p = W[2], *sv = W[3], *v = W[4];
+    MFB_CUDA(cudaMemcpyAsync(r0, r, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    for (double* w : {u, p, sv, v}) MFB_CUDA(cudaMemsetAsync(w, 0, n * sizeof(double), ctx->stream));
+    double rho = 1.0, rhobar, alpha, beta;
+    while (true) {
+        rhobar = rho;
+        MFB_TRY(V.dot(r, r0, &rho));
+        beta = rho / rhobar;
+        MFB_TRY(V.set(sv, {1.0, beta}, {r, p}));                          // s = r + beta p
+        MFB_TRY(S.lincomb(u, beta * beta, 2, std::initializer_list<double>{1.0, beta}.begin(),
+                          std::initializer_list<const double*>{sv, p}.begin()));   // u = s + beta (p + beta u)
+        MFB_TRY(S.mul(v, u));
+        double d;
+        MFB_TRY(V.dot(v, r0, &d));
+        alpha = rho / d;
+        MFB_TRY(V.set(p, {1.0, -alpha}, {sv, v}));                        // p = s - alpha v
+        MFB_TRY(V.add(x, {alpha, alpha}, {p, sv}));                       // x += alpha (p + s)
+        MFB_TRY(true_residual(S, r, b, x, &res));
+        iter++;
+        if (res <= tol || iter > maxiter) { *iters = iter; return MFB_OK; }
+    }
+}
+
+// cgs2!  (07_CGS.jl:52-105). Vectors: r0, s0 (random), u, w, s, v, t, c.
+int cgs2(Solver& S, double* x, const double* b, double* r, double tol, int maxiter, uint64_t seed, int pass,
+         std::vector<double*>& W, int* iters) {
+    mfb_ctx* ctx = S.ctx;
+    const int64_t n = S.n;
+    Vec V{S};
+    double res;
+    MFB_TRY(true_residual(S, r, b, x, &res));
+    if (res <= tol) { *iters = 0; return MFB_OK; }
+    int iter = 1;
+    double *r0 = W[0], *s0 = W[1], *u = W[2], *w = W[3], *sv = W[4], *v = W[5], *t = W[6], *c = W[7];
+    MFB_CUDA(cudaMemcpyAsync(r0, r, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    LAUNCH(k_rand, RED_BLOCKS, TPB, s0, n, (unsigned long long)seed, (unsigned long long)(pass * 64 + 62), ctx->gid.p, ctx->n_var);
+    for (double* z : {u, w, sv, v, t, c}) MFB_CUDA(cudaMemsetAsync(z, 0, n * sizeof(double), ctx->stream));
+    double alpha = 1, alphabar = 1, beta, betabar, rho, rhobar, sigma = 1, sigmabar = 1;
+    while (true) {
+        const double* da[2] = {r, r};
+        const double* db[2] = {r0, s0};
+        MFB_TRY(S.dots(2, da, db));
+        rho = ctx->h_scal[0];
+        rhobar = ctx->h_scal[1];
+        beta = 1 / alphabar * rho / sigma;
+        MFB_TRY(V.set(v, {1.0, beta}, {r, u}));                           // v = r + beta u
+        betabar = 1 / alpha * rhobar / sigmabar;
+        MFB_TRY(V.set(t, {1.0, betabar}, {r, sv}));                       // t = r + betabar s
+        MFB_TRY(S.lincomb(w, beta * betabar, 2, std::initializer_list<double>{1.0, beta}.begin(),
+                          std::initializer_list<const double*>{t, u}.begin()));    // w = t + beta (u + betabar w)
+        MFB_TRY(S.mul(c, w));
+        const double* ea[2] = {c, c};
+        MFB_TRY(S.dots(2, ea, db));
+        sigma = ctx->h_scal[0];
+        sigmabar = ctx->h_scal[1];
+        alpha = rho / sigma;
+        alphabar = rhobar / sigmabar;
+        MFB_TRY(V.set(sv, {1.0, -alpha}, {t, c}));                        // s = t - alpha c
+        MFB_TRY(V.set(u, {1.0, -alphabar}, {v, c}));                      // u = v - alphabar c
+        MFB_TRY(V.add(x, {alpha, alphabar}, {v, sv}));                    // x += alpha v + alphabar s
+        MFB_TRY(true_residual(S, r, b, x, &res));
+        iter++;
+        if (res <= tol || iter > maxiter) { *iters = iter; return MFB_OK; }
+    }
+}
+
+// tfqmr!  (08_QMR.jl:3-76). Vectors: r0, r_cgs, p, q, u, v, d, tmp.
+int tfqmr(Solver& S, double* x, const double* b, double* r, double tol, int maxiter, int checkiter, std::vector<double*>& W,
+          int* iters) {
+    mfb_ctx* ctx = S.ctx;
+    const int64_t n = S.n;
+    Vec V{S};
+    double res;
+    MFB_TRY(true_residual(S, r, b, x, &res));
+    if (res <= tol) { *iters = 0; return MFB_OK; }
+    int iter = 1;
+    double *r0 = W[0], *rc = W[1], *p = W[2], *q = W[3], *u = W[4], *v = W[5], *d = W[6], *tmp = W[7];
+    for (double* z : {r0, rc, p, u}) MFB_CUDA(cudaMemcpyAsync(z, r, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    for (double* z : {q, d, tmp}) MFB_CUDA(cudaMemsetAsync(z, 0, n * sizeof(double), ctx->stream));
+    MFB_TRY(S.mul(v, p));
+    double rr;
+    MFB_TRY(V.dot(r, r, &rr));
+    double r_norm = std::sqrt(rr), r_norm_old, tau = r_norm, rho = rr, rhobar, theta = 0.0, eta = 0.0, alpha, beta, c;
+    while (true) {
+        double dv;
+        MFB_TRY(V.dot(v, r0, &dv));
+        alpha = rho / dv;
+        MFB_TRY(V.set(q, {1.0, -alpha}, {u, v}));                         // q = u - alpha v
+        MFB_TRY(V.set(v, {1.0, 1.0}, {u, q}));                            // v = u + q
+        MFB_TRY(S.mul(tmp, v));
+        double n2;
+        MFB_TRY(V.add(rc, {-alpha}, {tmp}, &n2));                         // r_cgs -= alpha tmp
+        r_norm_old = r_norm;
+        r_norm = std::sqrt(n2);
+        MFB_TRY(S.lincomb(d, theta * theta * eta / alpha, 1, std::initializer_list<double>{1.0}.begin(),
+                          std::initializer_list<const double*>{u}.begin()));       // d = u + (theta^2 eta / alpha) d
+        theta = r_norm_old / tau;
+        c = 1 / std::sqrt(1 + theta * theta);
+        tau *= theta * c;
+        eta = c * c * alpha;
+        MFB_TRY(V.add(x, {eta}, {d}));
+        MFB_TRY(S.lincomb(d, theta * theta * eta / alpha, 1, std::initializer_list<double>{1.0}.begin(),
+                          std::initializer_list<const double*>{q}.begin()));       // d = q + (theta^2 eta / alpha) d
+        theta = std::sqrt(r_norm * r_norm_old) / tau;
+        c = 1 / std::sqrt(1 + theta * theta);
+        tau *= theta * c;
+        eta = c * c * alpha;
+        MFB_TRY(V.add(x, {eta}, {d}));
+        rhobar = rho;
+        MFB_TRY(V.dot(rc, r0, &rho));
+        beta = rho / rhobar;
+        MFB_TRY(V.set(u, {1.0, beta}, {rc, q}));                          // u = r_cgs + beta q
+        MFB_TRY(S.lincomb(p, beta * beta, 2, std::initializer_list<double>{1.0, beta}.begin(),
+                          std::initializer_list<const double*>{u, q}.begin()));    // p = u + beta (q + beta p)
+        MFB_TRY(S.mul(v, p));
+        iter++;
+        if (iter > maxiter) { *iters = iter; return MFB_OK; }
+        if (iter % checkiter == 0) {
+            MFB_TRY(true_residual(S, r, b, x, &res));
+            if (res <= tol) { *iters = iter; return MFB_OK; }
+        }
+    }
+}
+
+// lsqr!  (06_LSQR.jl:10-73). Vectors: u, v, w, tmp.
+int lsqr(Solver& S, double* x, const double* b, double* r, double tol, int maxiter, std::vector<double*>& W, int* iters) {
+    mfb_ctx* ctx = S.ctx;
+    const int64_t n = S.n;
+    Vec V{S};
+    double res;
+    MFB_TRY(true_residual(S, r, b, x, &res));
+    if (res <= tol) { *iters = 0; return MFB_OK; }
+    int iter = 1;
+    double *u = W[0], *v = W[1], *w = W[2], *tmp = W[3];
+    double n2;
+    MFB_TRY(V.dot(r, r, &n2));
+    double beta = std::sqrt(n2);
+    MFB_TRY(V.set(u, {1.0 / beta}, {r}));
+    MFB_TRY(S.tmul(v, u));
+    MFB_TRY(V.dot(v, v, &n2));
+    double alpha = std::sqrt(n2);
+    if (alpha != 0) MFB_TRY(V.set(v, {1.0 / alpha}, {v}));
+    MFB_CUDA(cudaMemcpyAsync(w, v, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    double phibar = beta, rhobar = alpha;
+    while (true) {
+        MFB_TRY(S.mul(tmp, v));
+        MFB_TRY(S.lincomb(u, -alpha, 1, std::initializer_list<double>{1.0}.begin(),
+                          std::initializer_list<const double*>{tmp}.begin(), &n2));           // u = Pl(A v) - alpha u
+        beta = std::sqrt(n2);
+        if (beta != 0) {
+            MFB_TRY(V.set(u, {1.0 / beta}, {u}));
+            MFB_TRY(S.tmul(tmp, u));
+            MFB_TRY(S.lincomb(v, -beta, 1, std::initializer_list<double>{1.0}.begin(),
+                              std::initializer_list<const double*>{tmp}.begin(), &n2));       // v = Pl(A' u) - beta v
+            alpha = std::sqrt(n2);
+            if (alpha != 0) MFB_TRY(V.set(v, {1.0 / alpha}, {v}));
+        }
+        const double rho = std::sqrt(rhobar * rhobar + beta * beta);
+        const double c = rhobar / rho, sn = beta / rho, theta = sn * alpha;
+        rhobar = -c * alpha;
+        const double phi = c * phibar;
+        phibar = sn * phibar;
+        MFB_TRY(V.add(x, {phi / rho}, {w}));
+        MFB_TRY(S.lincomb(w, -theta / rho, 1, std::initializer_list<double>{1.0}.begin(),
+                          std::initializer_list<const double*>{v}.begin()));                  // w = v - (theta / rho) w
+        iter++;
+        MFB_TRY(true_residual(S, r, b, x, &res));
+        if (res <= tol || iter > maxiter) { *iters = iter; return MFB_OK; }
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-extern "C" int mfb_krylov_solve(mfb_ctx* ctx, int method, int s, int maxiter, int max_pass, double tol, uint64_t seed,
-                                double* delta_out, mfb_solve_info* info) {
+extern "C" int mfb_krylov_solve_ex(mfb_ctx* ctx, int method, int s, int maxiter, int max_pass, double tol, uint64_t seed,
+                                   int pr_mode, int pl_mode, int checkiter, double* delta_out, mfb_solve_info* info) {
     if (!ctx) return MFB_ERR_ARG;
     MFB_REQUIRE(ctx->U > 0 && ctx->K_total.p, MFB_ERR_STATE, "mfb_krylov_solve: pattern/matrix not built");
-    MFB_REQUIRE(method == MFB_IDRS || method == MFB_BICGSTABL_GS, MFB_ERR_ARG, "unknown Krylov method");
-    MFB_REQUIRE(s >= 1 && 3 * s + 4 <= MAXT && s <= MAXD, MFB_ERR_ARG, "s out of range");
+    MFB_REQUIRE(method >= MFB_IDRS && method <= MFB_LSQR, MFB_ERR_ARG, "unknown Krylov method");
+    MFB_REQUIRE(pr_mode >= MFB_PR_JACOBI && pr_mode <= MFB_PR_IDENTITY && pl_mode >= MFB_PL_IDENTITY && pl_mode <= MFB_PL_JACOBI_ROW,
+                MFB_ERR_ARG, "unknown preconditioner mode");
+    MFB_REQUIRE(s >= 1 && (method == MFB_GMRES ? s + 1 <= MAXT : (3 * s + 4 <= MAXT && s <= MAXD)), MFB_ERR_ARG, "s out of range");
+    MFB_REQUIRE(!(mfb_is_distributed(ctx) && (pr_mode == MFB_PR_JACOBI_COLUMN || pl_mode == MFB_PL_JACOBI_ROW)), MFB_ERR_ARG,
+                "row/column-norm Jacobi needs assembled rows: not available on a partitioned mesh");
     MFB_CUDA(cudaSetDevice(ctx->device));
     MFB_TRY(ensure_scalars(ctx));
     ProfScope ps(ctx, MFB_T_SOLVE);
     const int nv = ctx->n_var;
     const int64_t n = ctx->N * nv;
     const int64_t nval = ctx->U * nv * nv;
-    // workspace: [0] Ks (scaled copy), then vectors
-    const int nvec = (method == MFB_IDRS ? 3 * s + 1 : 2 * s + 2) + 3;  // + x, r, (spare)
+    // work vectors of the method (beyond x and r)
+    int nw = 0;
+    switch (method) {
+        case MFB_IDRS: nw = 3 * s + 1; break;
+        case MFB_BICGSTABL_GS: case MFB_BICGSTABL: nw = 2 * s + 2; break;
+        case MFB_GMRES: nw = s + 1; break;
+        case MFB_CGS: nw = 5; break;
+        case MFB_CGS2: case MFB_TFQMR: nw = 8; break;
+        case MFB_LSQR: nw = 4; break;
+    }
+    const int nvec = nw + 3;  // + x, r, (spare)
     MFB_TRY(ensure_work(ctx, nvec, n));
     DevBuf<double> Ks;  // scaled matrix copy, freed on return (the reference allocates K_vals per solve too)
+    DevBuf<double> plv; // Pl_Jacobi vector
     MFB_CUDA(Ks.alloc(nval));
     MFB_CUDA(ctx->jac.alloc(n));
     MFB_CUDA(ctx->delta.alloc(n));
-    {
-        std::vector<int> diag_ok(nv);
-        for (int v = 0; v < nv; ++v) diag_ok[v] = ctx->block_of[v * nv + v] >= 0;
-        DevBuf<int> d_ok;
-        MFB_CUDA(d_ok.alloc(nv));
-        MFB_CUDA(cudaMemcpyAsync(d_ok.p, diag_ok.data(), nv * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        LAUNCH(k_jacobi_diag, nblk(n), TPB, ctx->nodeptr.p, ctx->nodecol.p, ctx->K_total.p, d_ok.p, ctx->N, nv,
-               mfb_is_distributed(ctx) ? ctx->owned.p : (const unsigned char*)nullptr, ctx->jac.p);
+    std::vector<int> diag_ok(nv);
+    for (int v = 0; v < nv; ++v) diag_ok[v] = ctx->block_of[v * nv + v] >= 0;
+    DevBuf<int> d_ok;
+    MFB_CUDA(d_ok.alloc(nv));
+    MFB_CUDA(cudaMemcpyAsync(d_ok.p, diag_ok.data(), nv * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned char* own = mfb_is_distributed(ctx) ? ctx->owned.p : (const unsigned char*)nullptr;
+    // ---- right preconditioner: Pr_Jacobi! (02_Preconditioner.jl:103-120) or Identity ----
+    if (pr_mode == MFB_PR_JACOBI) {
+        LAUNCH(k_jacobi_diag, nblk(n), TPB, ctx->nodeptr.p, ctx->nodecol.p, ctx->K_total.p, d_ok.p, ctx->N, nv, own, ctx->jac.p);
         MFB_TRY(mfb_halo_add(ctx, ctx->jac.p, nv));
         LAUNCH(k_jacobi_abs, nblk(n), TPB, ctx->jac.p, n);
-        LAUNCH(k_scale_copy, nblk(nval), TPB, ctx->nodecol.p, ctx->K_total.p, ctx->jac.p, nval, nv, Ks.p);
-        MFB_CUDA(cudaStreamSynchronize(ctx->stream));
-        d_ok.release();
+    } else if (pr_mode == MFB_PR_JACOBI_COLUMN) {
+        MFB_CUDA(cudaMemsetAsync(ctx->jac.p, 0, n * sizeof(double), ctx->stream));
+        LAUNCH(k_jacobi_sq, (unsigned)ctx->N, 32, ctx->nodeptr.p, ctx->nodecol.p, ctx->K_total.p, ctx->N, nv, 0, ctx->jac.p);
+        LAUNCH(k_sqrt, nblk(n), TPB, ctx->jac.p, n);
+    } else {
+        LAUNCH(k_fill1, nblk(n), TPB, ctx->jac.p, n);
     }
+    LAUNCH(k_scale_copy, nblk(nval), TPB, ctx->nodecol.p, ctx->K_total.p, ctx->jac.p, nval, nv, Ks.p);
+    // ---- left preconditioner: Pl_Jacobi (:150-166), computed from the already right-scaled matrix (:38-40) ----
+    if (pl_mode != MFB_PL_IDENTITY) {
+        MFB_CUDA(plv.alloc(n));
+        if (pl_mode == MFB_PL_JACOBI) {
+            LAUNCH(k_jacobi_diag, nblk(n), TPB, ctx->nodeptr.p, ctx->nodecol.p, Ks.p, d_ok.p, ctx->N, nv, own, plv.p);
+            MFB_TRY(mfb_halo_add(ctx, plv.p, nv));
+            LAUNCH(k_jacobi_abs, nblk(n), TPB, plv.p, n);
+        } else {
+            MFB_CUDA(cudaMemsetAsync(plv.p, 0, n * sizeof(double), ctx->stream));
+            LAUNCH(k_jacobi_sq, (unsigned)ctx->N, 32, ctx->nodeptr.p, ctx->nodecol.p, Ks.p, ctx->N, nv, 1, plv.p);
+            LAUNCH(k_sqrt, nblk(n), TPB, plv.p, n);
+        }
+    }
+    MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    d_ok.release();
     std::vector<double*> W(nvec - 2);
     for (int i = 0; i < nvec - 2; ++i) W[i] = ctx->work[i].p;
     double* x = ctx->work[nvec - 2].p;
@@ -685,6 +1192,7 @@ extern "C" int mfb_krylov_solve(mfb_ctx* ctx, int method, int s, int maxiter, in
     MFB_CUDA(cudaMemcpyAsync(r, b, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     Solver S{ctx, n, Ks.p};
     S.n_global = ctx->n_global_nodes * nv;
+    S.pl = plv.p;
     mfb_solve_info inf;
     memset(&inf, 0, sizeof(inf));
     {
@@ -693,13 +1201,29 @@ extern "C" int mfb_krylov_solve(mfb_ctx* ctx, int method, int s, int maxiter, in
         inf.initial_residual = S.nn(d);
     }
     int pass = 1;
-    double res = inf.initial_residual;
+    double res = inf.initial_residual, tol_factor = 1.0;
     while (true) {
         int it = 0;
-        if (method == MFB_IDRS) MFB_TRY(idrs(S, x, b, r, tol, maxiter, s, seed, pass, W, &it));
-        else MFB_TRY(bicgstabl_gs(S, x, b, r, tol, maxiter, s, seed, pass, W, &it));
+        const double ptol = tol_factor * tol;
+        switch (method) {
+            case MFB_IDRS: MFB_TRY(idrs(S, x, b, r, ptol, maxiter, s, seed, pass, W, &it)); break;
+            case MFB_BICGSTABL_GS: MFB_TRY(bicgstabl_gs(S, x, b, r, ptol, maxiter, s, seed, pass, W, &it)); break;
+            case MFB_BICGSTABL: MFB_TRY(bicgstabl_lu(S, x, b, r, ptol, maxiter, s, seed, pass, W, &it)); break;
+            case MFB_GMRES: MFB_TRY(gmres(S, x, b, r, ptol, maxiter, s, W, &it)); break;
+            case MFB_CGS: MFB_TRY(cgs(S, x, b, r, ptol, maxiter, W, &it)); break;
+            case MFB_CGS2: MFB_TRY(cgs2(S, x, b, r, ptol, maxiter, seed, pass, W, &it)); break;
+            case MFB_TFQMR: MFB_TRY(tfqmr(S, x, b, r, ptol, maxiter, checkiter > 0 ? checkiter : 200, W, &it)); break;
+            case MFB_LSQR: MFB_TRY(lsqr(S, x, b, r, ptol, maxiter, W, &it)); break;
+        }
         inf.iterations += it;
-        MFB_TRY(true_residual(S, r, b, x, &res));
+        MFB_TRY(true_residual(S, r, b, x, &res, false));        // the plain b - A x (:45-48)
+        if (S.pl) {                                              // left preconditioned: rescale the next pass's tolerance (:50-53)
+            MFB_TRY(S.Pl(r));
+            double d;
+            MFB_TRY(S.dot1(r, r, &d));
+            const double pres = S.nn(d);
+            tol_factor = std::min(pres / res, 1.0);
+        }
         if (res < tol || pass >= max_pass) break;
         pass++;
     }
@@ -718,8 +1242,14 @@ extern "C" int mfb_krylov_solve(mfb_ctx* ctx, int method, int s, int maxiter, in
     }
     MFB_CUDA(cudaStreamSynchronize(ctx->stream));
     Ks.release();
+    plv.release();
     if (info) *info = inf;
     return inf.converged ? MFB_OK : MFB_NOT_CONVERGED;
+}
+
+extern "C" int mfb_krylov_solve(mfb_ctx* ctx, int method, int s, int maxiter, int max_pass, double tol, uint64_t seed,
+                                double* delta_out, mfb_solve_info* info) {
+    return mfb_krylov_solve_ex(ctx, method, s, maxiter, max_pass, tol, seed, MFB_PR_JACOBI, MFB_PL_IDENTITY, 200, delta_out, info);
 }
 
 extern "C" int mfb_spmv(mfb_ctx* ctx, int which, const double* x, double* y, int64_t n) {

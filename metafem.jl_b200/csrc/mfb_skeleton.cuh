@@ -28,6 +28,7 @@
 #define MFB_MAX_CPV 24
 #define MFB_MAX_GLOBALS 16
 #define MFB_MAX_KPARAMS 4
+#define MFB_MAX_QP 16
 #endif
 
 struct MfbArgs {
@@ -52,6 +53,10 @@ struct MfbArgs {
     double Kp[MFB_MAX_KPARAMS];
     double glob[MFB_MAX_GLOBALS];
     const double* cpv[MFB_MAX_CPV];
+    // INTEGRATION_POINT_VAR arrays, [n_q, n_el] column-major in REFERENCE element order (domain blocks only)
+    const int* elem_ref;              // [n_items] reference element (0-based) of each internal element
+    const double* qpi[MFB_MAX_QP];    // read by the point function (outputs of the user callback)
+    double* qpo[MFB_MAX_QP];          // written by the argument-evaluation kernel (inputs of the user callback)
 };
 
 #ifdef __CUDACC__
@@ -82,24 +87,34 @@ __device__ __forceinline__ double inv3(const double (&J)[3][3], double (&I)[3][3
 //   static constexpr int NV, NA, NQ, L1 (= max_time_level + 1), BOUNDARY (0/1), LINEAR (0/1),
 //                        NW (inner words), NCW (cp words), NC (cp fields), HAS_RES, HAS_K, TPB,
 //                        NSD (dual slots used by K terms), KS (base slots used), ND (= NV*NSD*NV*KS dense tangent entries),
-//                        MT, NTC (register tile of the tangent contraction: MT rows x NTC columns per thread);
+//                        W (warps with tangent tiles), LPW (tiles = active lanes per warp), CG (column groups),
+//                        NTC (even; columns per tile, CG*NTC >= NA), SMEM (bytes);
 //   __device__ static constexpr int dslot(int i), bslot(int i);        // slot ids (0:N, 1..3: d/dx) of the used dual/base slots
-//   template <class S> __device__ static void words(const S& s, int q, double* w, double* c);
-//        // w[k] = interpolation of inner word k, c[k] = of CONTROLPOINT_VAR word k  (_Var_Basic)
-//   __device__ static void point(const double* w, const double* c, const double* nrm, const MfbArgs& A,
+//   __device__ static constexpr int wslot(int k), wlev(int k), wpos(int k);   // inner word k: slot, time level, variable
+//   __device__ static constexpr int cslot(int k), cfield(int k);              // cp word k: slot, field index
+//   static constexpr int EVAL (0/1), NQPI (integration-point words read), NQPO (callback arguments written);
+//   __device__ static void point(const double* w, const double* c, const double* nrm, const double* qv, const MfbArgs& A,
 //                                double* R /*[NV*4], zeroed*/, double* D /*[ND], zeroed*/);   // NOT yet weighted
+//   __device__ static void qp_eval(const double* w, const double* c, const MfbArgs& A, double* out /*[NQPO]*/);  // EVAL forms:
+//        // arguments of the user callback at this quadrature point (phase A of the two-phase update, 08_Tensor.jl:175-183)
 //        // D[((dp*NSD + dsi)*NV + bp)*KS + ksi] = d(residual integrand of dual (dp, dslot(dsi)))/d(word (bp, bslot(ksi))) * K_params[td]
 //
-// One thread block works on one item at a time (grid-stride over items); TPB threads.
-//   phase A  gather node data of the element into shared memory
-//   phase B  one thread per quadrature point: Jacobian, inverse, w*detJ (or facet normal and w*|t1 x t2|), physical
-//            gradients G[q][slot][a], interpolation of every word, emitted point function -> R[q][.], D[q][.] (weighted)
-//   phase C1 residual: r[a][v] = sum_q sum_slot G[q][slot][a] R[q][v][slot]                       (_Res_Basic)
-//   phase C2 tangent, sum-factorised per quadrature point (replaces one _Kval_Basic launch per term):
-//            stage 1  T[ks][(a,dp,bp)] = sum_dsi G[q][dslot(dsi)][a] * D[q][dp][dsi][bp][ks]       (NA*NV threads)
-//            stage 2  K[(a,dp,bp)][b] += sum_ks T[ks][(a,dp,bp)] * G[q][bslot(ks)][b]             (MT x NTC register tiles,
-//                     operands read from shared memory with 128-bit loads: 2 MT + NTC/2 wavefronts per MT*NTC DFMA)
-//            then red.global.add.f64 of the element matrix into the block-CSR values.
+// One thread block works on one item at a time (grid-stride over items); TPB threads, every phase uses all of them:
+//   phase A   gather node data of the element into shared memory
+//   phase B1  Jacobian J[q][i][X] = sum_a dN_X[q][a] x_i[a]                                  (NQ*9 outputs)
+//   phase B2  per q: inverse, w*detJ (facets: tangents, normal, w*|t1 x t2|)                 (NQ threads)
+//   phase B3  physical gradients G[q][slot][a]                                                (NQ*NA outputs)
+//   phase B4  interpolation of every word at every q (_Var_Basic)                             (NQ*(NW+NCW) outputs)
+//   phase B5  emitted point function -> R[q][.], D[q][.] (weighted)                           (NQ threads)
+//   phase C1  residual: r[a][v] = sum_q sum_slot G[q][slot][a] R[q][v][slot]                  (_Res_Basic)
+//   phase C2  tangent, sum-factorised per quadrature point (replaces one _Kval_Basic launch per term). One lane owns the
+//             NV x NTC tile of rows (a, dp, bp = 0..NV-1) and columns [cg*NTC, cg*NTC + NTC); no barrier and no shared-memory
+//             intermediate inside the q loop:
+//             stage 1  T[bp][ks] = sum_dsi G[q][dslot(dsi)][a] * D[q][dp][dsi][bp][ks]         (registers; D[q][dp][.] is one
+//                      contiguous, 16 B aligned run read with 128-bit loads, at most two distinct dp per warp)
+//             stage 2  acc[bp][c] += T[bp][ks] * G[q][bslot(ks)][cg*NTC + c]                   (G row: warp-uniform 128-bit loads)
+//   phase C3  element matrix -> shared memory -> red.global.add.f64 with the NV*NV entries of a node pair on adjacent
+//             lanes (72 contiguous bytes for NV = 3: ~3 L2 sectors per pair instead of 9).
 template <int NA>
 __device__ __forceinline__ double interp(const double* Ga /*[NA] contiguous*/, const double* u, int ustride) {
     double s = 0.0;
@@ -111,9 +126,32 @@ __device__ __forceinline__ double interp(const double* Ga /*[NA] contiguous*/, c
 template <class F>
 struct Smem {
     static constexpr int MROWS = F::NA * F::NV * F::NV;
-    double G[F::NQ][4][F::NA];                     // first two members stay 16 B aligned (even element counts)
-    double T[2][F::KS > 0 ? F::KS : 1][MROWS];
-    double D[F::NQ][F::ND > 0 ? F::ND : 1];
+    static constexpr int ND1 = F::ND > 0 ? F::ND : 1;
+    static constexpr int NWT = F::NW + F::NCW, NWT1 = NWT > 0 ? NWT : 1;
+    static constexpr int KS1 = F::KS > 0 ? F::KS : 1;
+    static constexpr int KLD = F::NA + 1 + (F::NA & 1);   // odd leading dimension: conflict-free strided reads in phase C3
+    static constexpr int NAP = F::NA + (F::NA & 1);        // G rows padded to an even length (16 B aligned rows)
+    static constexpr int DPB = F::NSD * F::NV * F::KS;     // tangent entries per dual variable dp ...
+    static constexpr int DPS = DPB + (DPB & 1);            // ... padded to an even stride
+    static constexpr int NDS = F::ND > 0 ? F::NV * DPS : 1;
+    struct alignas(16) GD {
+        double G[F::NQ][4][NAP];
+        double D[F::NQ][NDS];                      // D[q][dp][(dsi*NV + bp)*KS + ks], dp stride DPS
+    };
+    struct alignas(16) Geo {
+        double I[F::NQ][9];                        // Jacobian, then its inverse
+        double wgt[F::NQ];
+        double nrm[F::NQ][3];
+        double w[F::NQ][NWT1];
+    };
+    union {
+        GD gd;
+        double Ke[F::HAS_K ? MROWS : 1][KLD];      // phase C3 staging (G and D are dead by then)
+    };
+    union {
+        Geo geo;                                   // phases B1..B5
+        int em[F::HAS_K ? F::NA * F::NA : 1];      // phase C: node pair -> block-CSR entry of this element
+    };
     double R[F::NQ][F::NV * 4];
     double xe[F::NA][3];
     double ue[F::L1][F::NA][F::NV];
@@ -125,8 +163,10 @@ template <class F>
 __device__ __forceinline__ void assemble(const MfbArgs& A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<F>& S = *reinterpret_cast<Smem<F>*>(smem_raw);
+    static_assert(sizeof(Smem<F>) <= F::SMEM, "emitter under-estimated the shared-memory footprint");
     const int tid = threadIdx.x;
-    constexpr int NA = F::NA, NQ = F::NQ, NV = F::NV, BB = NV * NV, MROWS = NA * NV * NV;
+    constexpr int NA = F::NA, NQ = F::NQ, NV = F::NV, BB = NV * NV, MROWS = NA * NV * NV, TPB = F::TPB;
+    constexpr int NWT = F::NW + F::NCW;
 
     for (long long item = blockIdx.x; item < A.n_items; item += gridDim.x) {
         long long e = item;
@@ -138,7 +178,7 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
         const double* ref = A.ref + (size_t)tab * 4 * NQ * NA;
         __syncthreads();  // previous item fully consumed
         // ---- phase A: gather node data ----------------------------------------------------
-        for (int a = tid; a < NA; a += F::TPB) {
+        for (int a = tid; a < NA; a += TPB) {
             int g = A.conn[e * NA + a];
             S.node[a] = g;
             S.xe[a][0] = A.xyz[3 * (size_t)g + 0];
@@ -146,31 +186,34 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
             S.xe[a][2] = A.xyz[3 * (size_t)g + 2];
         }
         if (!F::LINEAR) {
-            for (int i = tid; i < F::L1 * NA * NV; i += F::TPB) {
+            for (int i = tid; i < F::L1 * NA * NV; i += TPB) {
                 int v = i % NV, a = (i / NV) % NA, l = i / (NV * NA);
                 int g = A.conn[e * NA + a];
                 S.ue[l][a][v] = A.u[((size_t)l * A.N + g) * NV + v];
             }
         }
-        for (int i = tid; i < F::NC * NA; i += F::TPB) {
+        for (int i = tid; i < F::NC * NA; i += TPB) {
             int a = i % NA, c = i / NA;
             S.ce[c][a] = A.cpv[c][A.conn[e * NA + a]];
         }
         __syncthreads();
-        // ---- phase B: one thread per quadrature point -------------------------------------
-        for (int q = tid; q < NQ; q += F::TPB) {
-            double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-            for (int a = 0; a < NA; ++a) {
-                double d0 = ref[(1 * NQ + q) * NA + a], d1 = ref[(2 * NQ + q) * NA + a], d2 = ref[(3 * NQ + q) * NA + a];
+        // ---- phase B1: Jacobian J[q][i][X] = dx_i/dX -----------------------------------------
+        for (int o = tid; o < NQ * 9; o += TPB) {
+            const int q = o / 9, r = o - q * 9, i = r / 3, X = r - i * 3;
+            const double* dN = ref + ((1 + X) * NQ + q) * NA;
+            double s = 0.0;
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    double x = S.xe[a][i];
-                    J[i][0] += d0 * x;
-                    J[i][1] += d1 * x;
-                    J[i][2] += d2 * x;
-                }
-            }
-            double I[3][3];
+            for (int a = 0; a < NA; ++a) s += dN[a] * S.xe[a][i];
+            S.geo.I[q][r] = s;
+        }
+        __syncthreads();
+        // ---- phase B2: inverse, weight, normal -----------------------------------------------
+        for (int q = tid; q < NQ; q += TPB) {
+            double J[3][3], I[3][3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int X = 0; X < 3; ++X) J[i][X] = S.geo.I[q][i * 3 + X];
             double det = inv3(J, I);
             double wgt;
             double nrm[3] = {0, 0, 0};
@@ -190,111 +233,178 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
             } else {
                 wgt = A.wq[q] * det;
             }
-            for (int a = 0; a < NA; ++a) {
-                double d0 = ref[(1 * NQ + q) * NA + a], d1 = ref[(2 * NQ + q) * NA + a], d2 = ref[(3 * NQ + q) * NA + a];
-                S.G[q][0][a] = ref[(0 * NQ + q) * NA + a];
 #pragma unroll
-                for (int s = 0; s < 3; ++s) S.G[q][1 + s][a] = (d0 * I[0][s] + d1 * I[1][s]) + d2 * I[2][s];
+            for (int X = 0; X < 3; ++X)
+#pragma unroll
+                for (int s = 0; s < 3; ++s) S.geo.I[q][X * 3 + s] = I[X][s];
+            S.geo.wgt[q] = wgt;
+            S.geo.nrm[q][0] = nrm[0]; S.geo.nrm[q][1] = nrm[1]; S.geo.nrm[q][2] = nrm[2];
+        }
+        __syncthreads();
+        // ---- phase B3: physical gradients ----------------------------------------------------
+        for (int o = tid; o < NQ * NA; o += TPB) {
+            const int q = o / NA, a = o - q * NA;
+            const double d0 = ref[(1 * NQ + q) * NA + a], d1 = ref[(2 * NQ + q) * NA + a], d2 = ref[(3 * NQ + q) * NA + a];
+            const double* I = S.geo.I[q];
+            S.gd.G[q][0][a] = ref[(0 * NQ + q) * NA + a];
+#pragma unroll
+            for (int s = 0; s < 3; ++s) S.gd.G[q][1 + s][a] = (d0 * I[0 * 3 + s] + d1 * I[1 * 3 + s]) + d2 * I[2 * 3 + s];
+        }
+        __syncthreads();
+        // ---- phase B4: words at quadrature points (_Var_Basic) --------------------------------
+        if constexpr (NWT > 0) {
+            for (int o = tid; o < NQ * NWT; o += TPB) {
+                const int q = o / NWT, k = o - q * NWT;
+                double v;
+                if (k < F::NW) v = interp<NA>(&S.gd.G[q][F::wslot(k)][0], &S.ue[F::wlev(k)][0][F::wpos(k)], NV);
+                else v = interp<NA>(&S.gd.G[q][F::cslot(k - F::NW)][0], &S.ce[F::cfield(k - F::NW)][0], 1);
+                S.geo.w[q][k] = v;
             }
+            __syncthreads();
+        }
+        if constexpr (F::EVAL) {
+            // ---- argument arrays of the quadrature-point callback; nothing else to do for this item ----
+            const size_t qbase = (size_t)A.elem_ref[e] * NQ;
+            for (int q = tid; q < NQ; q += TPB) {
+                double w[F::NW > 0 ? F::NW : 1], c[F::NCW > 0 ? F::NCW : 1], out[F::NQPO > 0 ? F::NQPO : 1];
+#pragma unroll
+                for (int k = 0; k < F::NW; ++k) w[k] = S.geo.w[q][k];
+#pragma unroll
+                for (int k = 0; k < F::NCW; ++k) c[k] = S.geo.w[q][F::NW + k];
+                F::qp_eval(w, c, A, out);
+#pragma unroll
+                for (int k = 0; k < F::NQPO; ++k) A.qpo[k][qbase + q] = out[k];
+            }
+            continue;
+        }
+        // ---- phase B5: point function ----------------------------------------------------------
+        for (int q = tid; q < NQ; q += TPB) {
             double w[F::NW > 0 ? F::NW : 1], c[F::NCW > 0 ? F::NCW : 1];
-            F::words(S, q, w, c);
+#pragma unroll
+            for (int k = 0; k < F::NW; ++k) w[k] = S.geo.w[q][k];
+#pragma unroll
+            for (int k = 0; k < F::NCW; ++k) c[k] = S.geo.w[q][F::NW + k];
+            const double wgt = S.geo.wgt[q];
+            const double nrm[3] = {S.geo.nrm[q][0], S.geo.nrm[q][1], S.geo.nrm[q][2]};
+            double qv[F::NQPI > 0 ? F::NQPI : 1];
+            if constexpr (F::NQPI > 0) {
+                const size_t qbase = (size_t)A.elem_ref[e] * NQ;
+#pragma unroll
+                for (int k = 0; k < F::NQPI; ++k) qv[k] = A.qpi[k][qbase + q];
+            }
             double R[NV * 4], D[F::ND > 0 ? F::ND : 1];
 #pragma unroll
             for (int k = 0; k < NV * 4; ++k) R[k] = 0.0;
 #pragma unroll
             for (int k = 0; k < F::ND; ++k) D[k] = 0.0;
-            F::point(w, c, nrm, A, R, D);
+            F::point(w, c, nrm, qv, A, R, D);
 #pragma unroll
             for (int k = 0; k < NV * 4; ++k) S.R[q][k] = R[k] * wgt;
+            if constexpr (F::ND > 0) {
+                constexpr int DPB = Smem<F>::DPB, DPS = Smem<F>::DPS;
 #pragma unroll
-            for (int k = 0; k < F::ND; ++k) S.D[q][k] = D[k] * wgt;
+                for (int k = 0; k < F::ND; ++k) S.gd.D[q][(k / DPB) * DPS + (k % DPB)] = D[k] * wgt;
+            }
         }
-        __syncthreads();
+        __syncthreads();   // geo is dead from here on: its storage becomes em
+        constexpr int NEM = F::HAS_K ? (NA * NA + TPB - 1) / TPB : 1;
+        int emr[NEM];
+        if constexpr (F::HAS_K) {
+            const int* em = A.emap + e * (NA * NA);
+#pragma unroll
+            for (int k = 0; k < NEM; ++k) emr[k] = tid + k * TPB < NA * NA ? em[tid + k * TPB] : 0;   // in flight during C1
+        }
         // ---- phase C1: residual ------------------------------------------------------------
         if constexpr (F::HAS_RES) {
-            for (int i = tid; i < NA * NV; i += F::TPB) {
-                int v = i % NV, a = i / NV;
+            constexpr int QS = (TPB / (NA * NV)) < 1 ? 1 : ((TPB / (NA * NV)) > 4 ? 4 : (TPB / (NA * NV)));   // q-range split
+            constexpr int QCH = (NQ + QS - 1) / QS;
+            for (int i = tid; i < NA * NV * QS; i += TPB) {
+                const int part = i / (NA * NV), j = i - part * (NA * NV);
+                const int v = j % NV, a = j / NV;
+                const int q1 = (part + 1) * QCH < NQ ? (part + 1) * QCH : NQ;
                 double s = 0.0;
-                for (int q = 0; q < NQ; ++q) {
+                for (int q = part * QCH; q < q1; ++q) {
 #pragma unroll
-                    for (int sl = 0; sl < 4; ++sl) s += S.G[q][sl][a] * S.R[q][v * 4 + sl];
+                    for (int sl = 0; sl < 4; ++sl) s += S.gd.G[q][sl][a] * S.R[q][v * 4 + sl];
                 }
                 if (s != 0.0) red_add(A.res + (size_t)S.node[a] * NV + v, s);
             }
         }
         // ---- phase C2: tangent ---------------------------------------------------------------
         if constexpr (F::HAS_K) {
-            constexpr int MT = F::MT, NTC = F::NTC, KS = F::KS, NSD = F::NSD;
-            constexpr int NRG = (MROWS + MT - 1) / MT, NCG = (NA + NTC - 1) / NTC;
-            static_assert(NRG * NCG <= F::TPB, "tangent tiling needs more threads than the block has");
-            static_assert(MT % 2 == 0 && NTC % 2 == 0 && NA % 2 == 0 && MROWS % 2 == 0, "128-bit shared-memory loads need even tiles");
-            const int rg = tid % NRG, cg = tid / NRG;
-            const int m0 = rg * MT, b0 = cg * NTC;
-            const bool tile_on = tid < NRG * NCG;
-            double acc[MT][NTC];
 #pragma unroll
-            for (int r = 0; r < MT; ++r)
+            for (int k = 0; k < NEM; ++k)
+                if (tid + k * TPB < NA * NA) S.em[tid + k * TPB] = emr[k];
+            constexpr int NTC = F::NTC, KS = F::KS, NSD = F::NSD, CG = F::CG, LPW = F::LPW, NPAIR = NA * NV;
+            constexpr int DPB = Smem<F>::DPB, DPS = Smem<F>::DPS;
+            static_assert(NTC % 2 == 0 && CG * NTC >= NA && LPW <= 32 && F::W * LPW >= NPAIR * CG && F::W * 32 <= TPB, "bad tangent tiling");
+            const int lane = tid & 31, warp = tid >> 5;
+            const int t = warp * LPW + lane;                         // tile index: column group major, then dp, then node
+            const bool tile_on = warp < F::W && lane < LPW && t < NPAIR * CG;
+            const int cgi = tile_on ? t / NPAIR : 0, p = tile_on ? t - cgi * NPAIR : 0;
+            const int dp = p / NA, a = p - dp * NA;
+            const int b0 = cgi * NTC;
+            double acc[NV][NTC];
+#pragma unroll
+            for (int r = 0; r < NV; ++r)
 #pragma unroll
                 for (int c = 0; c < NTC; ++c) acc[r][c] = 0.0;
-            for (int q = 0; q < NQ; ++q) {
-                const int buf = q & 1;
-                // stage 1: thread (a, dp) fills T[ks][(a,dp,bp)] for all bp, ks
-                for (int i = tid; i < NA * NV; i += F::TPB) {
-                    const int a = i / NV, dp = i - a * NV;
+            if (tile_on) {
+#pragma unroll 1
+                for (int q = 0; q < NQ; ++q) {
+                    // stage 1 (registers): T[bp][ks] = sum_d G[q][dslot(d)][a] * D[q][dp][d][bp][ks]
                     double g[NSD > 0 ? NSD : 1];
 #pragma unroll
-                    for (int d = 0; d < NSD; ++d) g[d] = S.G[q][F::dslot(d)][a];
-                    const double* Dq = &S.D[q][dp * NSD * NV * KS];
+                    for (int d = 0; d < NSD; ++d) g[d] = S.gd.G[q][F::dslot(d)][a];
+                    double dv[DPS];
+                    const double2* Dq = reinterpret_cast<const double2*>(&S.gd.D[q][dp * DPS]);
+#pragma unroll
+                    for (int i = 0; i < DPS / 2; ++i) {
+                        const double2 v = Dq[i];
+                        dv[2 * i] = v.x; dv[2 * i + 1] = v.y;
+                    }
+                    double T[NV][KS > 0 ? KS : 1];
 #pragma unroll
                     for (int bp = 0; bp < NV; ++bp)
 #pragma unroll
                         for (int ks = 0; ks < KS; ++ks) {
-                            double t = 0.0;
+                            double tv = 0.0;
 #pragma unroll
-                            for (int d = 0; d < NSD; ++d) t += g[d] * Dq[(d * NV + bp) * KS + ks];
-                            S.T[buf][ks][(a * NV + dp) * NV + bp] = t;
+                            for (int d = 0; d < NSD; ++d) tv += g[d] * dv[(d * NV + bp) * KS + ks];
+                            T[bp][ks] = tv;
                         }
-                }
-                __syncthreads();   // T[buf] complete; T[buf^1] (read in the previous iteration) may now be overwritten next time
-                if (tile_on) {
+                    // stage 2: rank-KS update of the lane's NV x NTC tile
 #pragma unroll
                     for (int ks = 0; ks < KS; ++ks) {
-                        double ta[MT], gb[NTC];
-                        const double2* tp = reinterpret_cast<const double2*>(&S.T[buf][ks][m0]);
-                        const double2* gp = reinterpret_cast<const double2*>(&S.G[q][F::bslot(ks)][b0]);
-#pragma unroll
-                        for (int r = 0; r < MT / 2; ++r) {
-                            const bool ok = m0 + 2 * r < MROWS;
-                            double2 v = ok ? tp[r] : make_double2(0.0, 0.0);
-                            ta[2 * r] = v.x; ta[2 * r + 1] = v.y;
-                        }
+                        const double2* gp = reinterpret_cast<const double2*>(&S.gd.G[q][F::bslot(ks)][b0]);
 #pragma unroll
                         for (int c = 0; c < NTC / 2; ++c) {
-                            const bool ok = b0 + 2 * c < NA;
-                            double2 v = ok ? gp[c] : make_double2(0.0, 0.0);
-                            gb[2 * c] = v.x; gb[2 * c + 1] = v.y;
+                            const double2 v = gp[c];
+#pragma unroll
+                            for (int bp = 0; bp < NV; ++bp) {
+                                acc[bp][2 * c] += T[bp][ks] * v.x;
+                                acc[bp][2 * c + 1] += T[bp][ks] * v.y;
+                            }
                         }
-#pragma unroll
-                        for (int r = 0; r < MT; ++r)
-#pragma unroll
-                            for (int c = 0; c < NTC; ++c) acc[r][c] += ta[r] * gb[c];
                     }
                 }
             }
+            __syncthreads();        // every warp is done with G, D and R: their storage becomes Ke
+            // ---- phase C3: stage the element matrix, then scatter with node-pair blocks on adjacent lanes ----
             if (tile_on) {
 #pragma unroll
-                for (int r = 0; r < MT; ++r) {
-                    const int m = m0 + r;
-                    if (m >= MROWS) break;
-                    const int a = m / BB, rem = m - a * BB;
-                    const int* em = A.emap + e * (NA * NA) + a * NA + b0;
+                for (int bp = 0; bp < NV; ++bp)
 #pragma unroll
-                    for (int c = 0; c < NTC; ++c) {
-                        if (b0 + c >= NA) break;
-                        const double v = acc[r][c];
-                        if (v != 0.0) red_add(A.Kval + (size_t)em[c] * BB + rem, v);
-                    }
-                }
+                    for (int c = 0; c < NTC; ++c)
+                        if (b0 + c < NA) S.Ke[a * BB + dp * NV + bp][b0 + c] = acc[bp][c];
+            }
+            __syncthreads();
+#pragma unroll 4
+            for (int i = tid; i < MROWS * NA; i += TPB) {
+                const int p = i / BB, k = i - p * BB;          // node pair p = a*NA + b, entry k = dp*NV + bp of its block
+                const int a = p / NA, b = p - a * NA;
+                const double v = S.Ke[a * BB + k][b];
+                if (v != 0.0) red_add(A.Kval + (size_t)S.em[p] * BB + k, v);
             }
         }
     }

@@ -19,16 +19,34 @@ def _slot(sd):
     return 0 if not sd else int(sd[0])
 
 
-def _tile(n_a, nv):
-    """Register tile (MT rows x NTC columns per thread) of the tangent contraction and the threads it needs."""
-    ntc = 10 if n_a % 10 == 0 else max(d for d in range(2, 11, 2) if n_a % d == 0)
-    mt = {1: 2, 2: 4, 3: 6, 4: 8}.get(nv, 2)
-    mrows = n_a * nv * nv
-    threads = -(-mrows // mt) * -(-n_a // ntc)
-    return mt, ntc, threads
+def _tile(n_a, nv, max_acc=60):
+    """Tangent tiling: one lane owns the rows (a, dp, bp = 0..NV-1) and NTC columns of the element matrix, i.e. NV*NTC
+    FP64 accumulators; CG column groups cover the NA columns (NTC even for 128-bit operand loads). The NA*NV*CG tiles
+    are dealt to W warps, LPW active lanes each."""
+    cg = 1
+    while True:
+        ntc = -(-n_a // cg)
+        ntc += ntc & 1
+        if nv * ntc <= max_acc or ntc == 2:
+            break
+        cg += 1
+    tiles = n_a * nv * cg
+    w = -(-tiles // 32)
+    return dict(NTC=ntc, CG=cg, W=w, LPW=-(-tiles // w))
 
 
-def _form(name, spec, blk, n_a, n_q, linear):
+def _table(fn, vals):
+    body = "{" + ", ".join(str(v) for v in (vals or [0])) + "}"
+    return f"  __device__ static constexpr int {fn}(int i) {{ constexpr int t[] = {body}; return t[i]; }}"
+
+
+def _align16(n):
+    return (n + 15) // 16 * 16
+
+
+def _form(name, spec, blk, n_a, n_q, linear, evalk=False):
+    """One Form struct. ``linear``: K_linear kernel; ``evalk``: argument-evaluation kernel of the quadrature-point
+    callbacks of the block (phase A of the two-phase nonlinear update); otherwise the residual + K_total kernel."""
     nv = len(spec["basic_vars"])
     L1 = spec["max_time_level"] + 1
     boundary = 1 if blk["kind"] == "boundary" else 0
@@ -36,6 +54,13 @@ def _form(name, spec, blk, n_a, n_q, linear):
     residues = [] if linear else blk["residues"]
     inner = [] if linear else blk["innervars"]
     ext = blk["extervars"]
+    calls = blk.get("qp_calls", [])
+    if evalk:
+        terms, residues = [], []
+    qpw = [] if (linear or evalk) else [w for w in ext if w["kind"] == "qp"]
+    qpo = [(a, n) for c in calls for a, n in zip(c["args"], c["arg_names"])] if evalk else []
+    if (qpw or qpo) and boundary:
+        raise ValueError("INTEGRATION_POINT_VAR words are supported in domain blocks only")
     cpw = [w for w in ext if w["kind"] == "cp"]
     fields = sorted({w["local"] for w in cpw})
     globs = [w["sym"] for w in ext if w["kind"] == "global"]
@@ -43,37 +68,52 @@ def _form(name, spec, blk, n_a, n_q, linear):
     bslots = sorted({_slot(t["deriv_sd"]) for t in terms})
     nsd, ks = len(dslots), len(bslots)
     nd = nv * nsd * nv * ks
-    mt, ntc, tile_threads = _tile(n_a, nv)
-    tpb = 32 * max(-(-tile_threads // 32) if terms else 1, -(-n_q // 32), 1)
+    tl = _tile(n_a, nv) if terms else dict(NTC=2, CG=1, W=1, LPW=1)
+    tpb = 32 * max(tl["W"] if terms else 2, 2)
     lines = []
     lines.append(f"struct {name} {{")
     lines.append(f"  static constexpr int NV = {nv}, NA = {n_a}, NQ = {n_q}, L1 = {L1}, BOUNDARY = {boundary}, "
                  f"LINEAR = {int(linear)}, NW = {len(inner)}, NCW = {len(cpw)}, NC = {len(fields)}, "
                  f"HAS_RES = {int(bool(residues))}, HAS_K = {int(bool(terms))}, TPB = {tpb}, "
-                 f"NSD = {nsd}, KS = {ks}, ND = {nd}, MT = {mt}, NTC = {ntc};")
-    for fn, sl in (("dslot", dslots), ("bslot", bslots)):
-        body = "{" + ", ".join(str(v) for v in (sl or [0])) + "}"
-        lines.append(f"  __device__ static constexpr int {fn}(int i) {{ constexpr int t[] = {body}; return t[i]; }}")
-    lines.append("  template <class S> __device__ static __forceinline__ void words(const S& s, int q, double* w, double* c) {")
-    for k, w in enumerate(inner):
-        lines.append(f"    w[{k}] = mfb::interp<NA>(&s.G[q][{_slot(w['sd'])}][0], &s.ue[{w['td']}][0][{w['pos']}], NV);")
-    for k, w in enumerate(cpw):
-        lines.append(f"    c[{k}] = mfb::interp<NA>(&s.G[q][{_slot(w['sd'])}][0], &s.ce[{fields.index(w['local'])}][0], 1);")
-    lines.append("  }")
+                 f"NSD = {nsd}, KS = {ks}, ND = {nd}, NTC = {tl['NTC']}, CG = {tl['CG']}, W = {tl['W']}, "
+                 f"LPW = {tl['LPW']}, SMEM = @SMEM@, "
+                 f"EVAL = {int(evalk)}, NQPI = {len(qpw)}, NQPO = {len(qpo)};")
+    lines.append(_table("dslot", dslots))
+    lines.append(_table("bslot", bslots))
+    lines.append(_table("wslot", [_slot(w["sd"]) for w in inner]))
+    lines.append(_table("wlev", [w["td"] for w in inner]))
+    lines.append(_table("wpos", [w["pos"] for w in inner]))
+    lines.append(_table("cslot", [_slot(w["sd"]) for w in cpw]))
+    lines.append(_table("cfield", [fields.index(w["local"]) for w in cpw]))
+    if evalk:
+        lines.append("  __device__ static __forceinline__ void qp_eval(const double* w, const double* c, const MfbArgs& A, "
+                     "double* out) {")
+        for k, w in enumerate(inner):
+            lines.append(f"    const double {w['sym']} = w[{k}];")
+        for k, w in enumerate(cpw):
+            lines.append(f"    const double {w['sym']} = c[{k}];")
+        for w in ext:
+            if w["kind"] == "global":
+                lines.append(f"    const double {w['sym']} = A.glob[{globs.index(w['sym'])}];")
+        for k, (a, _) in enumerate(qpo):
+            lines.append(f"    out[{k}] = {a};")
+        lines.append("  }")
     lines.append("  __device__ static __forceinline__ void point(const double* w, const double* c, const double* nrm, "
-                 "const MfbArgs& A, double* R, double* D) {")
-    for k, w in enumerate(inner):
+                 "const double* qv, const MfbArgs& A, double* R, double* D) {")
+    for k, w in enumerate([] if evalk else inner):
         lines.append(f"    const double {w['sym']} = w[{k}];")
-    for k, w in enumerate(cpw):
+    for k, w in enumerate([] if evalk else cpw):
         lines.append(f"    const double {w['sym']} = c[{k}];")
-    for w in ext:
+    for k, w in enumerate(qpw):
+        lines.append(f"    const double {w['sym']} = qv[{k}];")
+    for w in ([] if evalk else ext):
         if w["kind"] == "normal":
             lines.append(f"    const double {w['sym']} = nrm[{w['c'] - 1}];")
         elif w["kind"] == "global":
             lines.append(f"    const double {w['sym']} = A.glob[{globs.index(w['sym'])}];")
     known = {w["sym"] for w in inner} | {w["sym"] for w in ext}
     ident = re.compile(r"[A-Za-z_][A-Za-z_0-9]*")
-    for t in blk["temps"]:
+    for t in ([] if evalk else blk["temps"]):
         names = set(ident.findall(t["expr"])) - {"pow", "log", "exp", "sqrt", "fabs"}
         if all((n in known) or _is_number(n) for n in names):
             lines.append(f"    const double {t['sym']} = {t['expr']};")
@@ -86,10 +126,18 @@ def _form(name, spec, blk, n_a, n_q, linear):
         lines.append(f"    D[{idx}] += ({t['expr']}) * A.Kp[{t['deriv_td']}];")
     lines.append("  }")
     lines.append("};")
+    # shared-memory footprint of mfb::Smem<Form> (the skeleton static_asserts that this bound holds)
     mrows = n_a * nv * nv
-    smem = 8 * (n_q * 4 * n_a + 2 * max(ks, 1) * mrows + n_q * max(nd, 1) + n_q * nv * 4 + n_a * 3 + L1 * n_a * nv
-                + max(len(fields), 1) * n_a) + 4 * n_a + 32
-    return "\n".join(lines), fields, globs, smem, bool(terms), tpb
+    nap = n_a + (n_a & 1)
+    dpb = nsd * nv * ks
+    nds = nv * (dpb + (dpb & 1)) if nd else 1
+    gd = _align16(8 * (n_q * 4 * nap + n_q * nds))
+    ke = 8 * (mrows if terms else 1) * (nap + 1)
+    geo = _align16(max(8 * n_q * (9 + 1 + 3 + max(len(inner) + len(cpw), 1)), 4 * n_a * n_a if terms else 4))
+    smem = _align16(max(gd, ke)) + geo + 8 * (n_q * nv * 4 + n_a * 3 + L1 * n_a * nv
+                                             + max(len(fields), 1) * n_a) + 4 * n_a + 32
+    body = "\n".join(lines).replace("@SMEM@", str(smem))
+    return body, fields, globs, smem, bool(terms), tpb, [w["sym"] for w in qpw], [n for _, n in qpo]
 
 
 def _is_number(s):
@@ -98,6 +146,15 @@ def _is_number(s):
         return True
     except ValueError:
         return False
+
+
+def _min_blocks(tpb, smem, regs=184):
+    """Resident blocks per SM to ask of __launch_bounds__: what 227 KB of shared memory allow (1 KB reserved per block),
+    capped so that every thread keeps at least ``regs`` registers of the 64 K file."""
+    import os
+    if os.environ.get("MFB_MINB"):
+        return int(os.environ["MFB_MINB"])
+    return max(1, min(232448 // (smem + 1024), 65536 // (tpb * regs), 32))
 
 
 def emit(spec, n_a, n_q, n_qb, tpb=None):
@@ -109,25 +166,30 @@ def emit(spec, n_a, n_q, n_qb, tpb=None):
         nq = n_qb if blk["kind"] == "boundary" else n_q
         d = dict(kind=1 if blk["kind"] == "boundary" else 0, bg_ID=blk["bg_ID"], linear_kernel=None,
                  nonlinear_kernel=None, cp_var_names=[], global_names=[], threads_per_block=32, smem_bytes=0,
-                 has_nonlinear_K=0)
+                 has_nonlinear_K=0, eval_kernel=None, qp_in_names=[], qp_out_names=[])
         fields = globs = None
         variants = []
         if blk["linear_gradients"]:
             variants.append(("lin", True))
         if blk["residues"] or blk["nonlinear_gradients"]:
             variants.append(("nl", False))
-        forms = {tag: _form(f"F_b{i}_{tag}", spec, blk, n_a, nq, lin) for tag, lin in variants}
+        if blk.get("qp_calls"):
+            variants.append(("ev", False))
+        forms = {tag: _form(f"F_b{i}_{tag}", spec, blk, n_a, nq, lin, evalk=(tag == "ev")) for tag, lin in variants}
         # both kernels of a block are launched with the same shape
         block_tpb = max((f[5] for f in forms.values()), default=32)
         for tag, lin in variants:
-            body, fields, globs, smem, hask, _ = forms[tag]
+            body, fields, globs, smem, hask, _, qpin, qpout = forms[tag]
             body = re.sub(r"TPB = \d+", f"TPB = {block_tpb}", body, count=1)
-            src += [body, f'extern "C" __global__ void __launch_bounds__({block_tpb}) mfb_b{i}_{tag}(const MfbArgs A) '
+            src += [body, f'extern "C" __global__ void __launch_bounds__({block_tpb}, {_min_blocks(block_tpb, smem)}) mfb_b{i}_{tag}(const MfbArgs A) '
                           f'{{ mfb::assemble<F_b{i}_{tag}>(A); }}', ""]
-            d["linear_kernel" if lin else "nonlinear_kernel"] = f"mfb_b{i}_{tag}"
+            d[{"lin": "linear_kernel", "nl": "nonlinear_kernel", "ev": "eval_kernel"}[tag]] = f"mfb_b{i}_{tag}"
             d["smem_bytes"] = max(d["smem_bytes"], smem)
-            if not lin:
+            if tag == "nl":
                 d["has_nonlinear_K"] = int(hask)
+                d["qp_in_names"] = qpin
+            if tag == "ev":
+                d["qp_out_names"] = qpout
         d["threads_per_block"] = block_tpb
         d["cp_var_names"] = fields or []
         d["global_names"] = globs or []

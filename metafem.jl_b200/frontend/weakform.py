@@ -11,9 +11,14 @@ Spec layout (all positions 0-based, ``sd`` = list of 1-based directions like the
   max_time_level    highest td_order of any unknown word
   sparse_mapping    list of [dual_pos, base_pos]; index = block number (:70-74,104-105)
   globals / cp_vars names of GLOBAL_VAR scalars / CONTROLPOINT_VAR nodal arrays
+  qp_vars           names of INTEGRATION_POINT_VAR arrays ([n_q, n_el], one value per quadrature point)
   blocks            [domain, boundary groups...] each with innervars, extervars, temps,
                     residues, linear_gradients, nonlinear_gradients; expressions are C
                     expressions over the word symbols (also valid Python under numpy).
+                    qp_calls: user callbacks at quadrature points (J2Plasticity.jl:55: ``ep{i,j} =
+                    strain_updater(e{1,1}, ...)``; 08_Tensor.jl:175-183,210): func name, C expressions of
+                    the arguments, names of the argument arrays the two-phase update fills, names of the
+                    INTEGRATION_POINT_VAR outputs the residual then reads as external words (kind "qp").
 """
 import sympy as sp
 from sympy.printing.c import C99CodePrinter
@@ -70,6 +75,8 @@ class Physics:
         self.cp = {}         # Symbol -> (local, sd)
         self.normal = {}     # Symbol -> c
         self.glob = {}       # Symbol -> name
+        self.qp = {}         # Symbol -> name (INTEGRATION_POINT_VAR outputs of a callback)
+        self.qp_calls = []   # dict(func, args [sympy], outs [Symbol])
         self.forms = []
 
     # -- word constructors ---------------------------------------------------------------
@@ -92,6 +99,15 @@ class Physics:
         s = sp.Symbol(name, real=True)
         self.glob[s] = name
         return s
+
+    def qpcall(self, func, args, out_names):
+        """``outs = Main.func(args...)`` evaluated on whole [n_q, n_el] arrays (08_Tensor.jl:175-183,210); the outputs
+        are external INTEGRATION_POINT_VAR words: zero variation (09_Differentiation.jl:68-69)."""
+        outs = [sp.Symbol(n, real=True) for n in out_names]
+        for o in outs:
+            self.qp[o] = o.name
+        self.qp_calls.append(dict(func=func, args=[sp.sympify(a) for a in args], outs=outs))
+        return outs
 
     def form(self, kind, bg_ID=0):
         f = Form(kind, bg_ID)
@@ -116,7 +132,8 @@ class Physics:
                     wb, wtd, wsd = self.inner[w]
                     ent = dict(dual_pos=pos[db], dual_sd=list(dsd), deriv_pos=pos[wb], deriv_td=wtd,
                                deriv_sd=list(wsd), expr=de)
-                    (nonlin if any(s in self.inner for s in de.free_symbols) else lin).append(ent)
+                    # linear only without inner words and without integration-point externals (02_LocalAssembly.jl:49)
+                    (nonlin if any(s in self.inner or s in self.qp for s in de.free_symbols) else lin).append(ent)
                     sparse.add((pos[db], pos[wb]))
             res = _merge(res, ("dual_pos", "dual_sd"))
             lin = _merge(lin, ("dual_pos", "dual_sd", "deriv_pos", "deriv_td", "deriv_sd"))
@@ -135,6 +152,14 @@ class Physics:
                 used |= e_.free_symbols
             for t in res + lin + nonlin:
                 t["expr"] = cexpr(t["expr"])
+            calls = []
+            for c in self.qp_calls:
+                if any(o in used for o in c["outs"]):
+                    for a in c["args"]:
+                        used |= a.free_symbols
+                    calls.append(dict(func=c["func"], args=[cexpr(a) for a in c["args"]],
+                                      arg_names=[f"{c['func']}_arg{k + 1}" for k in range(len(c["args"]))],
+                                      outs=[o.name for o in c["outs"]]))
             inner = [dict(sym=s.name, pos=pos[self.inner[s][0]], td=self.inner[s][1], sd=list(self.inner[s][2]))
                      for s in sorted((s for s in used if s in self.inner), key=lambda s: s.name)]
             ext = []
@@ -145,12 +170,15 @@ class Physics:
                     ext.append(dict(sym=s.name, kind="normal", c=self.normal[s]))
                 elif s in self.glob:
                     ext.append(dict(sym=s.name, kind="global"))
+                elif s in self.qp:
+                    ext.append(dict(sym=s.name, kind="qp"))
             blocks.append(dict(kind=f.kind, bg_ID=f.bg_ID, innervars=inner, extervars=ext, temps=temps,
-                               residues=res, linear_gradients=lin, nonlinear_gradients=nonlin))
+                               residues=res, linear_gradients=lin, nonlinear_gradients=nonlin, qp_calls=calls))
         cp_vars = sorted({v[0] for v in self.cp.values()})
         return dict(dim=self.dim, basic_vars=basic_vars, max_time_level=max_td,
                     sparse_mapping=[list(p) for p in sorted(sparse)],
-                    globals=sorted(self.glob.values()), cp_vars=cp_vars, blocks=blocks)
+                    globals=sorted(self.glob.values()), cp_vars=cp_vars, qp_vars=sorted(self.qp.values()),
+                    blocks=blocks)
 
 
 def _merge(terms, keys):
@@ -272,4 +300,36 @@ def thermo_elasticity(E=210e3, nu=0.0, tau_b=None, rho=1e3, c=0.01, h=100.0, C=1
     for i in (1, 2, 3):
         f.add(f"d{i}", (), tau_b * P.u(f"d{i}"))
     P.form("boundary", thermal_bg).add("T", (), h * (T - P.cpvar("Te")))
+    return P.spec()
+
+
+def j2_plasticity(E=100e3, nu=0.0, rho=1e3, c=2.0, tau_b=None, L_box=1.0, fixed_bg=1, traction_bg=2):
+    """examples/hypo_elastic_plasticity/J2Plasticity.jl:44-63: small-strain J2 flow with the plastic strain ``ep`` an
+    INTEGRATION_POINT_VAR produced by the user callback ``strain_updater`` (the return map, :118-198); second time
+    derivatives (max_time_level = 2). ``ep`` has zero variation, so the tangent is the constant elastic one and lands
+    in K_linear together with the inertia/damping terms."""
+    lam, mu = E * nu / ((1 + nu) * (1 - 2 * nu)), E / (2 * (1 + nu))
+    tau_b = 1000 * E / L_box ** 2 if tau_b is None else tau_b
+    P = Physics(3)
+    gd = [[P.u(f"d{i}", 0, (j,)) for j in (1, 2, 3)] for i in (1, 2, 3)]
+    e = [[(gd[i][j] + gd[j][i]) / 2 for j in range(3)] for i in range(3)]
+    # ep{i,j} = strain_updater(e{1,1}, e{1,2}, e{1,3}, e{2,2}, e{2,3}, e{3,3}); six outputs in Voigt order (08_Tensor.jl:160)
+    epv = P.qpcall("strain_updater", [e[0][0], e[0][1], e[0][2], e[1][1], e[1][2], e[2][2]],
+                   [f"ep{k}" for k in range(1, 7)])
+    ep = [[epv[_VOIGT[(i + 1, j + 1)] - 1] for j in range(3)] for i in range(3)]
+    ee = [[e[i][j] - ep[i][j] for j in range(3)] for i in range(3)]
+    tr = ee[0][0] + ee[1][1] + ee[2][2]
+    sig = [[2 * mu * ee[i][j] + (lam * tr if i == j else 0) for j in range(3)] for i in range(3)]
+    dom = P.form("domain")
+    for i in range(3):
+        for j in range(3):
+            dom.add(f"d{i+1}", (j + 1,), sig[i][j])                                    # Bilinear(d{i;j}, sigma{i,j})
+    for i in (1, 2, 3):
+        dom.add(f"d{i}", (), rho * (c * P.u(f"d{i}", 1) + P.u(f"d{i}", 2)))           # rho (c d_i,t + d_i,tt)
+    f = P.form("boundary", fixed_bg)
+    for i in (1, 2, 3):
+        f.add(f"d{i}", (), tau_b * (P.u(f"d{i}") - P.cpvar(f"dw{i}")))
+    f = P.form("boundary", traction_bg)
+    for i in (1, 2, 3):
+        f.add(f"d{i}", (), -sum(P.cpvar(f"sl{_VOIGT[(i, j)]}") * P.n(j) for j in (1, 2, 3)))
     return P.spec()

@@ -12,7 +12,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmetafem_b200.so")
 
 MFB_OK, MFB_NOT_CONVERGED = 0, 1
-MFB_IDRS, MFB_BICGSTABL_GS = 0, 1
+MFB_IDRS, MFB_BICGSTABL_GS, MFB_BICGSTABL, MFB_GMRES, MFB_CGS, MFB_CGS2, MFB_TFQMR, MFB_LSQR = range(8)
+PR_JACOBI, PR_JACOBI_COLUMN, PR_IDENTITY = 0, 1, 2
+PL_IDENTITY, PL_JACOBI, PL_JACOBI_ROW = 0, 1, 2
 VEC_X, VEC_DX, VEC_X_STAR, VEC_RESIDUE = 0, 1, 2, 3
 MAT_K_LINEAR, MAT_K_TOTAL = 0, 1
 
@@ -25,7 +27,13 @@ class BlockDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("bg_ID", C.c_int32), ("linear_kernel", C.c_char_p),
                 ("nonlinear_kernel", C.c_char_p), ("n_cp_vars", C.c_int32), ("cp_var_names", C.POINTER(C.c_char_p)),
                 ("n_globals", C.c_int32), ("global_names", C.POINTER(C.c_char_p)),
-                ("threads_per_block", C.c_int32), ("smem_bytes", C.c_int32), ("has_nonlinear_K", C.c_int32)]
+                ("threads_per_block", C.c_int32), ("smem_bytes", C.c_int32), ("has_nonlinear_K", C.c_int32),
+                ("eval_kernel", C.c_char_p), ("n_qp_in", C.c_int32), ("qp_in_names", C.POINTER(C.c_char_p)),
+                ("n_qp_out", C.c_int32), ("qp_out_names", C.POINTER(C.c_char_p))]
+
+
+class J2Params(C.Structure):
+    _fields_ = [("lam", C.c_double), ("mu", C.c_double), ("Eb", C.c_double), ("Ep", C.c_double), ("f_res", C.c_double)]
 
 
 class SolveInfo(C.Structure):
@@ -58,9 +66,18 @@ _SIGS = {
     "mfb_kernel_check": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
     "mfb_assemble_linear": (C.c_int, [_P, _P, C.c_int]),
     "mfb_assemble_nonlinear": (C.c_int, [_P, _P, C.c_int, C.c_double, C.c_double]),
+    "mfb_qp_array": (C.c_int, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "mfb_qp_set": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
+    "mfb_qp_get": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
+    "mfb_eval_qp_args": (C.c_int, [_P, C.c_double, C.c_double]),
+    "mfb_j2_init": (C.c_int, [_P, C.c_char_p, C.c_double, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]),
+    "mfb_j2_iterate_stress": (C.c_int, [_P, C.c_char_p, C.POINTER(J2Params), C.POINTER(C.c_int64)]),
+    "mfb_j2_update_states": (C.c_int, [_P, C.c_char_p]),
     "mfb_spmv": (C.c_int, [_P, C.c_int, _P, _P, C.c_int64]),
     "mfb_krylov_solve": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64, _P,
                                    C.POINTER(SolveInfo)]),
+    "mfb_krylov_solve_ex": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                      _P, C.POINTER(SolveInfo)]),
     "mfb_initialize_dx": (C.c_int, [_P, C.c_double, _P, C.c_int]),
     "mfb_update_x_star": (C.c_int, [_P, _P, C.c_int]),
     "mfb_update_dx": (C.c_int, [_P, _P, C.c_int, C.c_double]),

@@ -48,6 +48,7 @@ class Domain:
         self.beta_params = None
         self.K_params = None
         self.linear_solver = None
+        self.callbacks = {}      # quadrature-point callbacks (Main.<func> in the generated code, 08_Tensor.jl:210)
 
 
 def sd_slot(sd):
@@ -175,6 +176,14 @@ def _declare_vars(dom, blk, cx, which):
                                             np.ascontiguousarray(dom.cp[w["local"]]))
         elif w["kind"] == "normal":
             env[w["sym"]] = cx.normals[:, w["c"] - 1, :]
+    if which != "linear":
+        # INTEGRATION_POINT_VAR outputs: `(ep1, ..., ep6) = Main.strain_updater(e1_1, ...)` on whole arrays
+        # (08_Tensor.jl:175-183); oracle arrays are [n_sel, n_q] = the reference's column-major [n_q, n_sel]
+        for c in blk.get("qp_calls", []):
+            args = [np.ascontiguousarray(_eval(a, env, cx.w.shape)) for a in c["args"]]
+            outs = dom.callbacks[c["func"]](*args)
+            for n, v in zip(c["outs"], outs):
+                env[n] = v
     return env
 
 

@@ -86,22 +86,54 @@ def Pr_Jacobi(A):
     return jac
 
 
-def iterative_Solve(dom, Sv_func, max_pass=4, seed=1234, log=None, **kw):
-    """iterative_Solve! (:32-76), right Jacobi only (Pl = Identity)."""
+def Pr_Jacobi_column(A):
+    """Pr_Jacobi!(normalized_by_column = true): Jacobi2_By_Colomn + sqrt (:110-113,122-129)."""
+    jac = np.sqrt(np.bincount(A.col - 1, A.data ** 2, minlength=A.shape[0]))
+    A.data /= jac[A.col - 1]
+    return jac
+
+
+class Pl_Jacobi:
+    """Pl_Jacobi (:150-166) + _JacobiP (:91-98): b ./= jac_vec in place; by diagonal or by row norm (Jacobi_By_Row :169-176)."""
+    def __init__(self, A, normalized_by_row=False):
+        n = A.shape[0]
+        rows = np.repeat(np.arange(n), np.diff(A.ptr))
+        if normalized_by_row:
+            self.jac = np.sqrt(np.bincount(rows, A.data ** 2, minlength=n))
+        else:
+            self.jac = np.ones(n)
+            d = (A.col - 1) == rows
+            self.jac[rows[d]] = np.abs(A.data[d])
+
+    def __call__(self, b):
+        b /= self.jac
+        return b
+
+
+def Identity(b):
+    return b
+
+
+def iterative_Solve(dom, Sv_func, max_pass=4, seed=1234, log=None, Pr_func=Pr_Jacobi, Pl_func=None, **kw):
+    """iterative_Solve! (:32-76)."""
     gf = dom.globalfield
     A = asm.csr_operator(gf)          # K_vals = K_total[K_val_ids] (:35): a fresh copy, as in the reference
-    jac = Pr_Jacobi(A)
+    jac = Pr_func(A) if Pr_func is not None else np.ones(A.shape[0])
+    Pl = Pl_func(A) if Pl_func is not None else Identity
     b = gf.residue
     r = b.copy()
     x = np.zeros_like(b)
     rng = np.random.default_rng(seed)
     pass_number = 1
+    tol_factor = 1.0
     iters = []
     while True:
-        it = Sv_func(x, A, b, r, tol=gf.converge_tol, rng=rng, **kw)
+        it = Sv_func(x, A, b, r, tol=tol_factor * gf.converge_tol, rng=rng, Pl=Pl, **kw)
         iters.append(it)
         r[:] = b - A @ x
         res = normalized_norm(r)
+        if Pl_func is not None:       # :50-53
+            tol_factor = min(normalized_norm(Pl(r)) / res, 1.0)
         if log:
             log(f"pass {pass_number} with res = {res} iter = {it}.")
         if res < gf.converge_tol or pass_number >= max_pass:
@@ -120,8 +152,8 @@ def modify_Omega(v1, v2):                               # 04_IDRs.jl:1-8
     return omega * angle / rho if rho < angle else omega
 
 
-def idrs(x, A, b, r, tol, maxiter, s=4, rng=None, **kw):    # 04_IDRs.jl:26-95
-    r[:] = b - A @ x
+def idrs(x, A, b, r, tol, maxiter, s=4, rng=None, Pl=Identity, **kw):    # 04_IDRs.jl:26-95
+    r[:] = Pl(b - A @ x)
     if normalized_norm(r) <= tol:
         return 0
     it = 1
@@ -144,7 +176,7 @@ def idrs(x, A, b, r, tol, maxiter, s=4, rng=None, **kw):    # 04_IDRs.jl:26-95
                 Q += c[i - k] * U[i]
             V = r - V
             U[k] = Q + omega * V
-            G[k] = A @ U[k]
+            G[k] = Pl(A @ U[k])
             for i in range(k):
                 alpha = np.dot(P[i], G[k]) / M[i, i]
                 G[k] -= alpha * G[i]
@@ -158,7 +190,7 @@ def idrs(x, A, b, r, tol, maxiter, s=4, rng=None, **kw):    # 04_IDRs.jl:26-95
                 return it
             f[k + 1:] -= beta * M[k + 1:, k]
             it += 1
-        Ar = A @ r
+        Ar = Pl(A @ r)
         omega = modify_Omega(Ar, r)
         x += omega * r
         r -= omega * Ar
@@ -167,8 +199,8 @@ def idrs(x, A, b, r, tol, maxiter, s=4, rng=None, **kw):    # 04_IDRs.jl:26-95
         it += 1
 
 
-def bicgstabl_GS(x, A, b, r, tol, maxiter, s=2, rng=None, **kw):   # 03_BiCGstabl.jl:18-96
-    r[:] = b - A @ x
+def bicgstabl_GS(x, A, b, r, tol, maxiter, s=2, rng=None, Pl=Identity, **kw):   # 03_BiCGstabl.jl:18-96
+    r[:] = Pl(b - A @ x)
     if normalized_norm(r) <= tol:
         return 0
     it = 1
@@ -188,11 +220,11 @@ def bicgstabl_GS(x, A, b, r, tol, maxiter, s=2, rng=None, **kw):   # 03_BiCGstab
             rho0 = rho1
             for i in range(j + 1):
                 U[i][:] = R[i] - beta * U[i]
-            U[j + 1][:] = A @ U[j]
+            U[j + 1][:] = Pl(A @ U[j])
             alpha = rho0 / np.dot(r_shadow, U[j + 1])
             for i in range(j + 1):
                 R[i] -= alpha * U[i + 1]
-            R[j + 1][:] = A @ R[j]
+            R[j + 1][:] = Pl(A @ R[j])
             x += alpha * U[0]
         for j in range(s):
             for i in range(j):
@@ -215,4 +247,220 @@ def bicgstabl_GS(x, A, b, r, tol, maxiter, s=2, rng=None, **kw):   # 03_BiCGstab
             R[0] -= gamp[j] * R[j + 1]
         it += s
         if normalized_norm(R[0]) <= tol or it >= maxiter:
+            return it
+
+
+# ---------------------------------------------------------------------------------------------
+# the remaining exported Krylov methods; Pl(.) follows every product as in the reference
+def _tmul(A, x):
+    """tmul! = A' x (06_LSQR.jl:25,42) through scipy on the oracle's CSR arrays."""
+    import scipy.sparse as sps
+    n = A.shape[0]
+    return sps.csr_matrix((A.data, A.col - 1, A.ptr - 1), shape=(n, n)).T @ x
+
+
+def bicgstabl(x, A, b, r, tol, maxiter, s=2, rng=None, Pl=Identity, **kw):   # 03_BiCGstabl.jl:98-162
+    r[:] = Pl(b - A @ x)
+    if np.linalg.norm(r) <= tol:
+        return 0
+    it = 1
+    n = len(b)
+    omega = rho0 = 1.0
+    alpha = 0.0
+    r_shadow = rng.random(n)
+    R = [r] + [np.zeros(n) for _ in range(s)]
+    U = [np.zeros(n) for _ in range(s + 1)]
+    M = np.zeros((s + 1, s + 1))
+    while True:
+        rho0 *= -omega
+        for j in range(s):
+            rho1 = np.dot(r_shadow, R[j])
+            beta = alpha * rho1 / rho0
+            rho0 = rho1
+            for i in range(j + 1):
+                U[i][:] = R[i] - beta * U[i]
+            U[j + 1][:] = Pl(A @ U[j])
+            alpha = rho0 / np.dot(r_shadow, U[j + 1])
+            for i in range(j + 1):
+                R[i] -= alpha * U[i + 1]
+            R[j + 1][:] = Pl(A @ R[j])
+            x += alpha * U[0]
+        for j in range(s + 1):
+            for i in range(j + 1):
+                M[i, j] = M[j, i] = np.dot(R[i], R[j])
+        gam = np.linalg.solve(M[1:, 1:], M[1:, 0])
+        for i in range(s):
+            U[0] -= gam[i] * U[i + 1]
+            x += gam[i] * R[i]
+        for i in range(s):
+            R[0] -= gam[i] * R[i + 1]
+        omega = gam[s - 1]
+        it += s
+        if normalized_norm(R[0]) <= tol or it >= maxiter:
+            return it
+
+
+def gmres(x, A, b, r, tol, maxiter, s=20, Pl=Identity, **kw):                 # 05_GMRES.jl:46-101
+    r[:] = Pl(b - A @ x)
+    if normalized_norm(r) <= tol:
+        return 0
+    it = 1
+    n = len(b)
+    Q = [np.zeros(n) for _ in range(s + 1)]
+    while True:
+        H = np.zeros((s + 1, s))
+        y = np.zeros(s + 1)
+        y[0] = r_norm = np.linalg.norm(r)
+        Q[0][:] = r / r_norm
+        for i in range(1, s + 1):
+            Q[i][:] = Pl(A @ Q[i - 1])
+            for j in range(i):
+                H[j, i - 1] = np.dot(Q[j], Q[i])
+                Q[i] -= H[j, i - 1] * Q[j]
+            H[i, i - 1] = np.linalg.norm(Q[i])
+            Q[i] /= H[i, i - 1]
+        yy = np.linalg.lstsq(H, y, rcond=None)[0]        # Hessenberg(H, y): least squares by Givens rotations (:7-37)
+        for i in range(s):
+            x += Q[i] * yy[i]
+        it += s
+        r[:] = Pl(b - A @ x)
+        if normalized_norm(r) <= tol or it > maxiter:
+            return it
+
+
+def cgs(x, A, b, r, tol, maxiter, Pl=Identity, **kw):                         # 07_CGS.jl:10-50
+    r[:] = Pl(b - A @ x)
+    if normalized_norm(r) <= tol:
+        return 0
+    it = 1
+    r0 = r.copy()
+    n = len(b)
+    rho = 1.0
+    u, p, sv, v = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)      # FEM_buffer in the reference (uninitialised)
+    while True:
+        rhobar = rho
+        rho = np.dot(r, r0)
+        beta = rho / rhobar
+        sv[:] = r + beta * p
+        u[:] = sv + beta * (p + beta * u)
+        v[:] = Pl(A @ u)
+        alpha = rho / np.dot(v, r0)
+        p[:] = sv - alpha * v
+        x += alpha * (p + sv)
+        r[:] = Pl(b - A @ x)
+        it += 1
+        if normalized_norm(r) <= tol or it > maxiter:
+            return it
+
+
+def cgs2(x, A, b, r, tol, maxiter, rng=None, Pl=Identity, **kw):              # 07_CGS.jl:52-105
+    r[:] = Pl(b - A @ x)
+    if normalized_norm(r) <= tol:
+        return 0
+    it = 1
+    r0 = r.copy()
+    n = len(b)
+    s0 = rng.random(n)
+    alpha = alphabar = sigma = sigmabar = 1.0
+    u, w, sv, v, t, c = (np.zeros(n) for _ in range(6))
+    while True:
+        rho = np.dot(r, r0)
+        beta = 1 / alphabar * rho / sigma
+        v[:] = r + beta * u
+        rhobar = np.dot(r, s0)
+        betabar = 1 / alpha * rhobar / sigmabar
+        t[:] = r + betabar * sv
+        w[:] = t + beta * (u + betabar * w)
+        c[:] = Pl(A @ w)
+        sigma = np.dot(c, r0)
+        alpha = rho / sigma
+        sv[:] = t - alpha * c
+        sigmabar = np.dot(c, s0)
+        alphabar = rhobar / sigmabar
+        u[:] = v - alphabar * c
+        x += alpha * v + alphabar * sv
+        r[:] = Pl(b - A @ x)
+        it += 1
+        if normalized_norm(r) <= tol or it > maxiter:
+            return it
+
+
+def tfqmr(x, A, b, r, tol, maxiter, checkiter=200, Pl=Identity, **kw):        # 08_QMR.jl:3-76
+    r[:] = Pl(b - A @ x)
+    if normalized_norm(r) <= tol:
+        return 0
+    it = 1
+    n = len(b)
+    r0, rc, p, u = r.copy(), r.copy(), r.copy(), r.copy()
+    q, d = np.zeros(n), np.zeros(n)
+    v = Pl(A @ p)
+    r_norm = tau = np.linalg.norm(r)
+    rho = np.dot(r, r)
+    theta = eta = 0.0
+    while True:
+        alpha = rho / np.dot(v, r0)
+        q[:] = u - alpha * v
+        v[:] = u + q
+        rc -= alpha * Pl(A @ v)
+        r_norm_old, r_norm = r_norm, np.linalg.norm(rc)
+        d[:] = u + (theta ** 2 * eta / alpha) * d
+        theta = r_norm_old / tau
+        c = 1 / np.sqrt(1 + theta ** 2)
+        tau *= theta * c
+        eta = c ** 2 * alpha
+        x += eta * d
+        d[:] = q + (theta ** 2 * eta / alpha) * d
+        theta = np.sqrt(r_norm * r_norm_old) / tau
+        c = 1 / np.sqrt(1 + theta ** 2)
+        tau *= theta * c
+        eta = c ** 2 * alpha
+        x += eta * d
+        rhobar, rho = rho, np.dot(rc, r0)
+        beta = rho / rhobar
+        u[:] = rc + beta * q
+        p[:] = u + beta * (q + beta * p)
+        v[:] = Pl(A @ p)
+        it += 1
+        if it > maxiter:
+            return it
+        if it % checkiter == 0:
+            r[:] = Pl(b - A @ x)
+            if normalized_norm(r) <= tol:
+                return it
+
+
+def lsqr(x, A, b, r, tol, maxiter, Pl=Identity, **kw):                        # 06_LSQR.jl:10-73
+    r[:] = Pl(b - A @ x)
+    if normalized_norm(r) <= tol:
+        return 0
+    it = 1
+    u = r.copy()
+    beta = np.linalg.norm(u)
+    u /= beta
+    v = Pl(_tmul(A, u))
+    alpha = np.linalg.norm(v)
+    if alpha != 0:
+        v /= alpha
+    w = v.copy()
+    phibar, rhobar = beta, alpha
+    while True:
+        u[:] = Pl(A @ v) - alpha * u
+        beta = np.linalg.norm(u)
+        if beta != 0:
+            u /= beta
+            v[:] = Pl(_tmul(A, u)) - beta * v
+            alpha = np.linalg.norm(v)
+            if alpha != 0:
+                v /= alpha
+        rho = np.sqrt(rhobar ** 2 + beta ** 2)
+        c, sn = rhobar / rho, beta / rho
+        theta = sn * alpha
+        rhobar = -c * alpha
+        phi = c * phibar
+        phibar = sn * phibar
+        x += (phi / rho) * w
+        w[:] = v - (theta / rho) * w
+        it += 1
+        r[:] = Pl(b - A @ x)
+        if normalized_norm(r) <= tol or it > maxiter:
             return it

@@ -51,6 +51,8 @@ def spec_for(name):
         return wf.neo_hookean(fixed_bg=1, traction_bg=2)
     if name == "thermo_elasticity":
         return wf.thermo_elasticity(fixed_bg=1, thermal_bg=3)
+    if name == "j2":
+        return wf.j2_plasticity(fixed_bg=1, traction_bg=2)
     raise KeyError(name)
 
 
@@ -87,6 +89,15 @@ def build_case(name, n=(3, 2, 2), size=(1.5, 1.0, 1.0), seed=0):
             dom.cp[b + "_t1"][:] = 1e-4 * mesh.x[(i + 2) % 3]
         dom.globalfield.dt = 1.0
         dom.globalfield.converge_tol = 1e-6
+    elif name == "j2":
+        # strains around 1e-3: part of the quadrature points are beyond the yield surface (Y = 100, E = 1e5)
+        for i, b in enumerate(("d1", "d2", "d3")):
+            dom.cp[b][:] = 4e-4 * np.sin(1.3 * mesh.x[(i + 1) % 3] + 0.2 * i) * mesh.x[0] + rng.uniform(-1e-5, 1e-5, N) * h
+            dom.cp[b + "_t1"][:] = 1e-4 * mesh.x[(i + 2) % 3]
+            dom.cp[b + "_t2"][:] = 1e-5 * mesh.x[i]
+        dom.cp["sl1"][:] = 120.0
+        dom.globalfield.dt = 1.0
+        dom.globalfield.converge_tol = 1e-3
     else:
         for i, b in enumerate(("d1", "d2", "d3")):
             dom.cp[b][:] = 0.02 * np.sin(1.3 * mesh.x[(i + 1) % 3] + 0.2 * i) * mesh.x[0] + rng.uniform(-1e-3, 1e-3, N) * h
@@ -115,3 +126,20 @@ def product_from_oracle(dom, device=0):
 
 def rel(a, b):
     return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+J2_PARAMS = dict(Y_initial=100.0, lam=0.0, mu=50e3, Eb=12.5e3, Ep=25e3, f_res=1.0)   # J2Plasticity.jl:46-50,199-203 (group 2)
+
+
+def j2_states(dom, fd=None):
+    """The example's strain_updater on both sides: oracle MaterialState (numpy) and the library's built-in return map."""
+    from oracle import j2 as oj2
+    n_el, n_q = dom.mesh.controlpoint_IDs.shape[1], dom.mesh.space.ref_itp_vals.shape[0]
+    ost = oj2.MaterialState((n_el, n_q), **J2_PARAMS)
+    dom.callbacks["strain_updater"] = ost
+    pst = None
+    if fd is not None:
+        import metafem_b200 as m
+        pst = m.api.J2MaterialState(fd, **J2_PARAMS)
+        fd.callbacks["strain_updater"] = pst
+    return ost, pst

@@ -1,0 +1,74 @@
+"""All exported Krylov methods and preconditioner modes of iterative_Solve! on the CUDA path (through the C ABI), against
+a direct solve and the oracle's restatement of the same method: solver-tolerance parity (random shadow vectors differ)."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spl
+
+from helpers import build_case, product_from_oracle
+from oracle import assembly as oasm, solver as osv
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", params=["thermal", "linear_elasticity"])
+def system(request, built_lib):
+    import metafem_b200 as m
+    dom, spec, mesh = build_case(request.param, (3, 2, 2))
+    oasm.assemble_Global_Variables(dom)
+    fd = product_from_oracle(dom)
+    m.assemble_Global_Variables(fd)
+    m.compile_Updater_GPU(1, fd)
+    osv.update_Time(dom)
+    osv.initialize_dx(dom)
+    oasm.K_linear_func(dom)
+    osv.update_x_star(dom)
+    oasm.K_nonlinear_func(dom)
+    td = fd.time_discretization
+    m.api.update_Time(fd.globalfield, td)
+    gam, al = np.array(td.gamma_params), np.array(td.alpha_params)
+    fd.ctx.call("mfb_initialize_dx", fd.globalfield.dt, m.lib.ptr(gam), len(gam))
+    fd.K_linear_func(td, fem_domain=fd)
+    fd.ctx.call("mfb_update_x_star", m.lib.ptr(al), len(al))
+    fd.K_nonlinear_func(td, fem_domain=fd)
+    gf = dom.globalfield
+    A = oasm.csr_from_globalfield(gf)
+    yield dom, fd, A, spl.spsolve(A.tocsc(), gf.residue)
+    fd.close()
+
+
+METHODS = [("idrs", dict(s=8)), ("bicgstabl_GS", dict(s=4)), ("bicgstabl", dict(s=4)), ("gmres", dict(s=20)), ("cgs", {}),
+           ("cgs2", {}), ("tfqmr", dict(checkiter=20)), ("lsqr", {})]
+
+
+def _check(dom, fd, A, exact, delta, odelta):
+    gf = dom.globalfield
+    assert fd.last_solve["converged"], fd.last_solve
+    r = gf.residue - A @ delta
+    assert np.linalg.norm(r) / np.sqrt(len(r)) < gf.converge_tol * 1.01
+    scale = np.linalg.norm(exact)
+    err_p, err_o = np.linalg.norm(delta - exact) / scale, np.linalg.norm(odelta - exact) / scale
+    assert err_p < max(100 * err_o, 1e-5), (err_p, err_o)
+
+
+@pytest.mark.parametrize("name,kw", METHODS, ids=[m[0] for m in METHODS])
+def test_method_parity(system, name, kw):
+    import metafem_b200 as m
+    dom, fd, A, exact = system
+    maxiter = 20000 if name == "lsqr" else 4000
+    delta = m.iterative_Solve(fd, Sv_func=name + "!", maxiter=maxiter, max_pass=10, want_delta=True, **kw)
+    odelta = osv.iterative_Solve(dom, getattr(osv, name), max_pass=10, maxiter=maxiter, **kw)
+    _check(dom, fd, A, exact, delta, odelta)
+
+
+MODES = [("Pr_Jacobi_column", "Identity", osv.Pr_Jacobi_column, None), ("Identity", "Identity", None, None),
+         ("Pr_Jacobi", "Pl_Jacobi", osv.Pr_Jacobi, osv.Pl_Jacobi),
+         ("Identity", "Pl_Jacobi_row", None, lambda A: osv.Pl_Jacobi(A, normalized_by_row=True))]
+
+
+@pytest.mark.parametrize("pr,pl,opr,opl", MODES, ids=[f"{a}-{b}" for a, b, _, _ in MODES])
+def test_preconditioner_modes(system, pr, pl, opr, opl):
+    import metafem_b200 as m
+    dom, fd, A, exact = system
+    delta = m.iterative_Solve(fd, Sv_func="bicgstabl_GS", Pr_func=pr, Pl_func=pl, maxiter=4000, max_pass=10, s=4, want_delta=True)
+    odelta = osv.iterative_Solve(dom, osv.bicgstabl_GS, max_pass=10, maxiter=4000, s=4, Pr_func=opr, Pl_func=opl)
+    _check(dom, fd, A, exact, delta, odelta)
