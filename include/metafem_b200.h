@@ -70,6 +70,9 @@ int mfb_synchronize(mfb_ctx *ctx);
 /* CUDA-event timers on the context's stream. ids: 0 SpMV, 1 K_nonlinear_func, 2 K_linear_func,
  * 3 Krylov solve, 4 domain element kernel, 7 boundary element kernels. mfb_profile_get sums and
  * clears them: ms[8], count[8]. */
+/* Measured FP64 FMA throughput of the device in TFLOP/s (register-resident FMA chains on every SM): the peak the
+ * FP64-bound element kernels are reported against. */
+int mfb_measure_fp64_peak(mfb_ctx *ctx, double *tflops);
 int mfb_profile_enable(mfb_ctx *ctx, int on);
 int mfb_profile_get(mfb_ctx *ctx, double *ms, int64_t *count);
 

@@ -125,6 +125,7 @@ struct mfb_ctx {
     // ---- krylov workspace ----
     std::vector<DevBuf<double>> work;
     DevBuf<double> jac, scal;   // Jacobi vector, device scalars
+    DevBuf<double> ksc;         // device-resident Krylov recurrence scalars
     double* h_scal = nullptr;   // pinned host mirror of scal
 
     // ---- staging ----

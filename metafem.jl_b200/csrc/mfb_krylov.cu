@@ -255,6 +255,7 @@ struct LinComb {
     int n;
     double c[MAXT];
     const double* x[MAXT];
+    const double* cp[MAXT];   // optional device-resident factor: term i is c[i] * (*cp[i]) * x_i  (nullptr -> c[i] * x_i)
 };
 
 // optional fused squared norm of the result (partials[block]); 4 independent elements per thread for memory-level parallelism
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(TPB) k_lincomb(LinComb L, int64_t n, double* p
             sv[u] = (L.ay != 0.0 && idx[u] >= 0) ? L.ay * L.y[idx[u]] : 0.0;
         }
         for (int k = 0; k < L.n; ++k) {
-            const double c = L.c[k];
+            const double c = L.cp[k] ? L.c[k] * __ldg(L.cp[k]) : L.c[k];
             const double* __restrict__ xp = L.x[k];
 #pragma unroll
             for (int u = 0; u < 4; ++u)
@@ -302,6 +303,8 @@ struct AxpbyBatch {
     double a[MAXT], b[MAXT];
     double* y[MAXT];
     const double* x[MAXT];
+    const double* ap[MAXT];   // optional device-resident factors of a_k and b_k (nullptr -> 1)
+    const double* bp[MAXT];
 };
 // y_k = a_k*y_k + b_k*x_k for k < n, independent updates in one launch
 __global__ void __launch_bounds__(TPB) k_axpby_batch(AxpbyBatch Bt, int64_t n) {
@@ -312,10 +315,12 @@ __global__ void __launch_bounds__(TPB) k_axpby_batch(AxpbyBatch Bt, int64_t n) {
         for (int k = 0; k < Bt.n; ++k) {
             double* __restrict__ yp = Bt.y[k];
             const double* __restrict__ xp = Bt.x[k];
+            const double ak = Bt.ap[k] ? Bt.a[k] * __ldg(Bt.ap[k]) : Bt.a[k];
+            const double bk = Bt.bp[k] ? Bt.b[k] * __ldg(Bt.bp[k]) : Bt.b[k];
             const double y0 = yp[i0], x0 = xp[i0];
             const double y1 = ok1 ? yp[i1] : 0.0, x1 = ok1 ? xp[i1] : 0.0;
-            yp[i0] = Bt.a[k] * y0 + Bt.b[k] * x0;
-            if (ok1) yp[i1] = Bt.a[k] * y1 + Bt.b[k] * x1;
+            yp[i0] = ak * y0 + bk * x0;
+            if (ok1) yp[i1] = ak * y1 + bk * x1;
         }
     }
 }
@@ -393,6 +398,47 @@ __global__ void k_rand(double* p, int64_t n, unsigned long long seed, unsigned l
         p[i] = (double)(h >> 11) * (1.0 / 9007199254740992.0);
     }
 }
+
+// ---- device-resident scalar recurrences of bicgstabl_GS! (03_BiCGstabl.jl:43-93): one thread, enqueued between the
+// vector kernels so that an outer iteration needs ONE host synchronisation (the convergence test) instead of 19.
+// sc layout: [0] rho0 [1] alpha [2] omega [3] beta [4] res2 [8 + j] sig [24 + j] gamp [40 + j] gam [56 + j] gampp [72 + i*S + j] tau
+enum { SC_RHO0 = 0, SC_ALPHA = 1, SC_OMEGA = 2, SC_BETA = 3, SC_RES2 = 4, SC_SIG = 8, SC_GAMP = 24, SC_GAM = 40, SC_GAMPP = 56,
+       SC_TAU = 72, SC_COUNT = 72 + 16 * 16 };
+__global__ void k_sc_init(double* sc) {
+    for (int i = threadIdx.x; i < SC_COUNT; i += blockDim.x) sc[i] = 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) { sc[SC_RHO0] = 1.0; sc[SC_OMEGA] = 1.0; sc[SC_ALPHA] = 0.0; }
+}
+__global__ void k_sc_outer_begin(double* sc) { sc[SC_RHO0] *= -sc[SC_OMEGA]; }                        // rho0 *= -omega (:44)
+__global__ void k_sc_beta(double* sc, const double* red) {                                            // (:46-48)
+    const double rho1 = red[0];
+    sc[SC_BETA] = sc[SC_ALPHA] * rho1 / sc[SC_RHO0];
+    sc[SC_RHO0] = rho1;
+}
+__global__ void k_sc_alpha(double* sc, const double* red) { sc[SC_ALPHA] = sc[SC_RHO0] / red[0]; }   // (:54)
+__global__ void k_sc_tau(double* sc, const double* red, int i, int j, int S) { sc[SC_TAU + i * S + j] = red[0] / sc[SC_SIG + i]; }  // (:66)
+__global__ void k_sc_sig(double* sc, const double* red, int j) {                                      // (:69-70)
+    sc[SC_SIG + j] = red[0];
+    sc[SC_GAMP + j] = red[1] / red[0];
+}
+__global__ void k_sc_gamma(double* sc, int S) {                                                       // (:72-81)
+    double* gam = sc + SC_GAM;
+    const double* gamp = sc + SC_GAMP;
+    const double* tau = sc + SC_TAU;
+    gam[S - 1] = gamp[S - 1];
+    sc[SC_OMEGA] = gam[S - 1];
+    for (int j = S - 2; j >= 0; --j) {
+        double d = 0.0;
+        for (int i = j + 1; i < S; ++i) d += tau[j * S + i] * gam[i];
+        gam[j] = gamp[j] - d;
+    }
+    for (int j = 0; j < S - 1; ++j) {
+        double d = 0.0;
+        for (int i = j + 1; i < S - 1; ++i) d += tau[j * S + i] * gam[i + 1];
+        sc[SC_GAMPP + j] = gam[j + 1] + d;
+    }
+}
+__global__ void k_sc_store(double* sc, int at, const double* red) { sc[at] = red[0]; }
 
 __global__ void k_div(double* y, const double* x, const double* d, int64_t n) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -486,6 +532,38 @@ struct Solver {
         MFB_CUDA(cudaStreamSynchronize(ctx->stream));
         return MFB_OK;
     }
+    // same reduction, results stay on the device in ctx->scal[0..k) (no host synchronisation)
+    int dots_dev(int k, const double* const* xs, const double* const* ys) {
+        MultiDot M;
+        M.n = k;
+        for (int i = 0; i < k; ++i) { M.x[i] = xs[i]; M.y[i] = ys[i]; }
+        double* partials = ctx->scal.p + 64;
+        LAUNCH(k_multidot, RED_BLOCKS, TPB, M, n, partials, mask(), ctx->n_var);
+        LAUNCH(k_reduce_partials, k, 256, partials, RED_BLOCKS, ctx->scal.p);
+        return mfb_allreduce_sum(ctx, ctx->scal.p, k);
+    }
+    // y = ay*y + sum (c_i * *cp_i) x_i with device-resident factors; optional fused ||y||^2 left in ctx->scal[0]
+    int lincomb_dev(double* y, double ay, int k, const double* c, const double* const* cp, const double* const* xs,
+                    bool norm2 = false) {
+        LinComb L;
+        L.y = y; L.ay = ay; L.n = k;
+        for (int i = 0; i < k; ++i) { L.c[i] = c[i]; L.cp[i] = cp[i]; L.x[i] = xs[i]; }
+        double* partials = norm2 ? ctx->scal.p + 64 : nullptr;
+        LAUNCH(k_lincomb, RED_BLOCKS, TPB, L, n, partials, mask(), ctx->n_var);
+        if (norm2) {
+            LAUNCH(k_reduce_partials, 1, 256, partials, RED_BLOCKS, ctx->scal.p);
+            MFB_TRY(mfb_allreduce_sum(ctx, ctx->scal.p, 1));
+        }
+        return MFB_OK;
+    }
+    int axpby_batch_dev(int k, double* const* ys, const double* a, const double* const* ap, const double* b,
+                        const double* const* bp, const double* const* xs) {
+        AxpbyBatch Bt;
+        Bt.n = k;
+        for (int i = 0; i < k; ++i) { Bt.y[i] = ys[i]; Bt.a[i] = a[i]; Bt.ap[i] = ap[i]; Bt.b[i] = b[i]; Bt.bp[i] = bp[i]; Bt.x[i] = xs[i]; }
+        LAUNCH(k_axpby_batch, RED_BLOCKS, TPB, Bt, n);
+        return MFB_OK;
+    }
     int dot1(const double* x, const double* y, double* out) {
         const double* xs[1] = {x};
         const double* ys[1] = {y};
@@ -497,7 +575,7 @@ struct Solver {
     int lincomb(double* y, double ay, int k, const double* c, const double* const* xs, double* norm2 = nullptr) {
         LinComb L;
         L.y = y; L.ay = ay; L.n = k;
-        for (int i = 0; i < k; ++i) { L.c[i] = c[i]; L.x[i] = xs[i]; }
+        for (int i = 0; i < k; ++i) { L.c[i] = c[i]; L.x[i] = xs[i]; L.cp[i] = nullptr; }
         double* partials = norm2 ? ctx->scal.p + 64 : nullptr;
         LAUNCH(k_lincomb, RED_BLOCKS, TPB, L, n, partials, mask(), ctx->n_var);
         if (norm2) {
@@ -512,7 +590,7 @@ struct Solver {
     int axpby_batch(int k, double* const* ys, const double* a, const double* b, const double* const* xs) {
         AxpbyBatch Bt;
         Bt.n = k;
-        for (int i = 0; i < k; ++i) { Bt.y[i] = ys[i]; Bt.a[i] = a[i]; Bt.b[i] = b[i]; Bt.x[i] = xs[i]; }
+        for (int i = 0; i < k; ++i) { Bt.y[i] = ys[i]; Bt.a[i] = a[i]; Bt.b[i] = b[i]; Bt.x[i] = xs[i]; Bt.ap[i] = Bt.bp[i] = nullptr; }
         LAUNCH(k_axpby_batch, RED_BLOCKS, TPB, Bt, n);
         return MFB_OK;
     }
@@ -641,6 +719,9 @@ int idrs(Solver& S, double* x, const double* b, double* r, double tol, int maxit
 }
 
 // bicgstabl_GS!  (03_BiCGstabl.jl:18-96). Vectors: R[1..s] (R[0] = r), U[0..s], r_shadow.
+// Same operations in the same order as the reference; the scalars (rho, alpha, beta, tau, sigma, gamma...) live on the
+// device and are updated by one-thread kernels between the vector kernels, so the stream never drains inside an outer
+// iteration: one host synchronisation per 2 s SpMVs (the convergence test) instead of one per dot product.
 int bicgstabl_gs(Solver& S, double* x, const double* b, double* r, double tol, int maxiter, int s, uint64_t seed,
                  int pass, std::vector<double*>& W, int* iters) {
     mfb_ctx* ctx = S.ctx;
@@ -649,6 +730,7 @@ int bicgstabl_gs(Solver& S, double* x, const double* b, double* r, double tol, i
     MFB_TRY(true_residual(S, r, b, x, &res));
     if (res <= tol) { *iters = 0; return MFB_OK; }
     int iter = 1;
+    if (s > 16) { ctx->err = "bicgstabl_GS: s > 16"; return MFB_ERR_ARG; }
     std::vector<double*> R(s + 1), U(s + 1);
     R[0] = r;
     for (int i = 1; i <= s; ++i) R[i] = W[i - 1];
@@ -657,74 +739,67 @@ int bicgstabl_gs(Solver& S, double* x, const double* b, double* r, double tol, i
     LAUNCH(k_rand, RED_BLOCKS, TPB, r_shadow, n, (unsigned long long)seed, (unsigned long long)(pass * 64 + 63), ctx->gid.p, ctx->n_var);
     for (int i = 1; i <= s; ++i) MFB_CUDA(cudaMemsetAsync(R[i], 0, n * sizeof(double), ctx->stream));
     for (int i = 0; i <= s; ++i) MFB_CUDA(cudaMemsetAsync(U[i], 0, n * sizeof(double), ctx->stream));
-    std::vector<double> gam(s, 0.0), gamp(s, 0.0), gampp(s, 0.0), sig(s, 0.0), tau(s * s, 0.0);
-    double omega = 1.0, rho0 = 1.0, alpha = 0.0;
+    MFB_CUDA(ctx->ksc.alloc(SC_COUNT));
+    double* sc = ctx->ksc.p;
+    const double* red = ctx->scal.p;
+    LAUNCH(k_sc_init, 1, 128, sc);
     std::vector<double*> yy(s + 2);
-    std::vector<const double*> xx(2 * s + 2);
+    std::vector<const double*> xx(2 * s + 2), pa(2 * s + 2), pb(2 * s + 2);
     std::vector<double> ca(2 * s + 2), cb(2 * s + 2);
     while (true) {
-        rho0 *= -omega;
+        LAUNCH(k_sc_outer_begin, 1, 1, sc);
         for (int j = 0; j < s; ++j) {
-            double rho1;
-            MFB_TRY(S.dot1(r_shadow, R[j], &rho1));
-            double beta = alpha * rho1 / rho0;
-            rho0 = rho1;
-            for (int i = 0; i <= j; ++i) { yy[i] = U[i]; ca[i] = -beta; cb[i] = 1.0; xx[i] = R[i]; }
-            MFB_TRY(S.axpby_batch(j + 1, yy.data(), ca.data(), cb.data(), xx.data()));
+            const double* d1x[1] = {r_shadow};
+            const double* d1y[1] = {R[j]};
+            MFB_TRY(S.dots_dev(1, d1x, d1y));
+            LAUNCH(k_sc_beta, 1, 1, sc, red);
+            for (int i = 0; i <= j; ++i) { yy[i] = U[i]; ca[i] = -1.0; pa[i] = sc + SC_BETA; cb[i] = 1.0; pb[i] = nullptr; xx[i] = R[i]; }
+            MFB_TRY(S.axpby_batch_dev(j + 1, yy.data(), ca.data(), pa.data(), cb.data(), pb.data(), xx.data()));   // U[i] = R[i] - beta U[i]
             MFB_TRY(S.mul(U[j + 1], U[j]));
-            double d;
-            MFB_TRY(S.dot1(r_shadow, U[j + 1], &d));
-            alpha = rho0 / d;
-            for (int i = 0; i <= j; ++i) { yy[i] = R[i]; ca[i] = 1.0; cb[i] = -alpha; xx[i] = U[i + 1]; }
-            yy[j + 1] = x; ca[j + 1] = 1.0; cb[j + 1] = alpha; xx[j + 1] = U[0];
-            MFB_TRY(S.axpby_batch(j + 2, yy.data(), ca.data(), cb.data(), xx.data()));
+            d1y[0] = U[j + 1];
+            MFB_TRY(S.dots_dev(1, d1x, d1y));
+            LAUNCH(k_sc_alpha, 1, 1, sc, red);
+            for (int i = 0; i <= j; ++i) { yy[i] = R[i]; ca[i] = 1.0; pa[i] = nullptr; cb[i] = -1.0; pb[i] = sc + SC_ALPHA; xx[i] = U[i + 1]; }
+            yy[j + 1] = x; ca[j + 1] = 1.0; pa[j + 1] = nullptr; cb[j + 1] = 1.0; pb[j + 1] = sc + SC_ALPHA; xx[j + 1] = U[0];
+            MFB_TRY(S.axpby_batch_dev(j + 2, yy.data(), ca.data(), pa.data(), cb.data(), pb.data(), xx.data()));   // R[i] -= alpha U[i+1]; x += alpha U[0]
             MFB_TRY(S.mul(R[j + 1], R[j]));
         }
         for (int j = 0; j < s; ++j) {
             for (int i = 0; i < j; ++i) {
-                double d;
-                MFB_TRY(S.dot1(R[i + 1], R[j + 1], &d));
-                tau[i * s + j] = d / sig[i];
-                double mt = -tau[i * s + j];
-                const double* x1[1] = {R[i + 1]};
-                MFB_TRY(S.lincomb(R[j + 1], 1.0, 1, &mt, x1));
+                const double* ax[1] = {R[i + 1]};
+                const double* ay[1] = {R[j + 1]};
+                MFB_TRY(S.dots_dev(1, ax, ay));
+                LAUNCH(k_sc_tau, 1, 1, sc, red, i, j, s);
+                const double m1 = -1.0;
+                const double* cp1[1] = {sc + SC_TAU + i * s + j};
+                MFB_TRY(S.lincomb_dev(R[j + 1], 1.0, 1, &m1, cp1, ax));                                          // R[j+1] -= tau_ij R[i+1]
             }
             const double* a2[2] = {R[j + 1], R[0]};
             const double* b2[2] = {R[j + 1], R[j + 1]};
-            MFB_TRY(S.dots(2, a2, b2));
-            sig[j] = ctx->h_scal[0];
-            gamp[j] = ctx->h_scal[1] / sig[j];
+            MFB_TRY(S.dots_dev(2, a2, b2));
+            LAUNCH(k_sc_sig, 1, 1, sc, red, j);
         }
-        gam[s - 1] = gamp[s - 1];
-        omega = gam[s - 1];
-        for (int j = s - 2; j >= 0; --j) {
-            double d = 0.0;
-            for (int i = j + 1; i < s; ++i) d += tau[j * s + i] * gam[i];
-            gam[j] = gamp[j] - d;
-        }
-        for (int j = 0; j < s - 1; ++j) {
-            double d = 0.0;
-            for (int i = j + 1; i < s - 1; ++i) d += tau[j * s + i] * gam[i + 1];
-            gampp[j] = gam[j + 1] + d;
-        }
+        LAUNCH(k_sc_gamma, 1, 1, sc, s);
         // x += gam[0]*R[0] + sum gampp[j]*R[j+1]      (uses R[0] before its update, as the reference does)
         int nt = 0;
-        ca[nt] = gam[0]; xx[nt++] = R[0];
-        for (int j = 0; j < s - 1; ++j) { ca[nt] = gampp[j]; xx[nt++] = R[j + 1]; }
-        MFB_TRY(S.lincomb(x, 1.0, nt, ca.data(), xx.data()));
+        ca[nt] = 1.0; pa[nt] = sc + SC_GAM; xx[nt++] = R[0];
+        for (int j = 0; j < s - 1; ++j) { ca[nt] = 1.0; pa[nt] = sc + SC_GAMPP + j; xx[nt++] = R[j + 1]; }
+        MFB_TRY(S.lincomb_dev(x, 1.0, nt, ca.data(), pa.data(), xx.data()));
         // U[0] -= gam[s-1]*U[s] + sum gam[j]*U[j+1]
         nt = 0;
-        ca[nt] = -gam[s - 1]; xx[nt++] = U[s];
-        for (int j = 0; j < s - 1; ++j) { ca[nt] = -gam[j]; xx[nt++] = U[j + 1]; }
-        MFB_TRY(S.lincomb(U[0], 1.0, nt, ca.data(), xx.data()));
+        ca[nt] = -1.0; pa[nt] = sc + SC_GAM + s - 1; xx[nt++] = U[s];
+        for (int j = 0; j < s - 1; ++j) { ca[nt] = -1.0; pa[nt] = sc + SC_GAM + j; xx[nt++] = U[j + 1]; }
+        MFB_TRY(S.lincomb_dev(U[0], 1.0, nt, ca.data(), pa.data(), xx.data()));
         // R[0] -= gamp[s-1]*R[s] + sum gamp[j]*R[j+1]   (+ fused norm)
         nt = 0;
-        ca[nt] = -gamp[s - 1]; xx[nt++] = R[s];
-        for (int j = 0; j < s - 1; ++j) { ca[nt] = -gamp[j]; xx[nt++] = R[j + 1]; }
-        double n2;
-        MFB_TRY(S.lincomb(R[0], 1.0, nt, ca.data(), xx.data(), &n2));
+        ca[nt] = -1.0; pa[nt] = sc + SC_GAMP + s - 1; xx[nt++] = R[s];
+        for (int j = 0; j < s - 1; ++j) { ca[nt] = -1.0; pa[nt] = sc + SC_GAMP + j; xx[nt++] = R[j + 1]; }
+        MFB_TRY(S.lincomb_dev(R[0], 1.0, nt, ca.data(), pa.data(), xx.data(), true));
+        MFB_CUDA(cudaMemcpyAsync(ctx->h_scal, ctx->scal.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        MFB_CUDA(cudaStreamSynchronize(ctx->stream));          // the one synchronisation of the outer iteration
+        const double n2 = ctx->h_scal[0];
         iter += s;
-        if (S.nn(n2) <= tol || iter >= maxiter) { *iters = iter; return MFB_OK; }
+        if (!(S.nn(n2) > tol) || iter >= maxiter) { *iters = iter; return MFB_OK; }   // also leaves on NaN (breakdown)
     }
 }
 

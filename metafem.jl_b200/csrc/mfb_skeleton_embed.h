@@ -100,41 +100,33 @@ __device__ __forceinline__ double inv3(const double (&J)[3][3], double (&I)[3][3
 //        // arguments of the user callback at this quadrature point (phase A of the two-phase update, 08_Tensor.jl:175-183)
 //        // D[((dp*NSD + dsi)*NV + bp)*KS + ksi] = d(residual integrand of dual (dp, dslot(dsi)))/d(word (bp, bslot(ksi))) * K_params[td]
 //
-// One thread block works on one item at a time (grid-stride over items); TPB threads, every phase uses all of them:
-//   phase A   gather node data of the element into shared memory
-//   phase B1  Jacobian J[q][i][X] = sum_a dN_X[q][a] x_i[a]                                  (NQ*9 outputs)
-//   phase B2  per q: inverse, w*detJ (facets: tangents, normal, w*|t1 x t2|)                 (NQ threads)
-//   phase B3  physical gradients G[q][slot][a]                                                (NQ*NA outputs)
-//   phase B4  interpolation of every word at every q (_Var_Basic)                             (NQ*(NW+NCW) outputs)
-//   phase B5  emitted point function -> R[q][.], D[q][.] (weighted)                           (NQ threads)
-//   phase C1  residual: r[a][v] = sum_q sum_slot G[q][slot][a] R[q][v][slot]                  (_Res_Basic)
-//   phase C2  tangent, sum-factorised per quadrature point (replaces one _Kval_Basic launch per term). One lane owns the
+// One thread block works on one item at a time (grid-stride over items); TPB threads:
+//   phase A   gather node data of the element into shared memory; prefetch the element's scatter map
+//   phase B1  one pass over the reference-element tables for BOTH the Jacobian and the fields: item (q, X) accumulates
+//             J[q][i][X] = sum_a dN_X[q][a] x_i[a] and the reference gradient (X = 0: the value) of every field
+//             component gu[q][var][X] = sum_a dN_X[q][a] u_var[a]                              (NQ*4 items; _Var_Basic)
+//   phase B2  per q: inverse Jacobian, w*detJ (facets: tangents, normal, w*|t1 x t2|)           (NQ threads)
+//   phase B3  warp 0: words at the q-points (gradient words = reference gradients x inverse Jacobian) and the emitted
+//             point function -> R[q][.], D[q][.] (weighted);  the other warps meanwhile: physical gradients
+//             G[q][slot][a] = dN[q][a] . I[q]                                                   (NQ*NA outputs)
+//   phase C   tangent, sum-factorised per quadrature point (replaces one _Kval_Basic launch per term). One lane owns the
 //             NV x NTC tile of rows (a, dp, bp = 0..NV-1) and columns [cg*NTC, cg*NTC + NTC); no barrier and no shared-memory
 //             intermediate inside the q loop:
 //             stage 1  T[bp][ks] = sum_dsi G[q][dslot(dsi)][a] * D[q][dp][dsi][bp][ks]         (registers; D[q][dp][.] is one
 //                      contiguous, 16 B aligned run read with 128-bit loads, at most two distinct dp per warp)
 //             stage 2  acc[bp][c] += T[bp][ks] * G[q][bslot(ks)][cg*NTC + c]                   (G row: warp-uniform 128-bit loads)
-//   phase C3  element matrix -> shared memory -> red.global.add.f64 with the NV*NV entries of a node pair on adjacent
-//             lanes (72 contiguous bytes for NV = 3: ~3 L2 sectors per pair instead of 9).
-template <int NA>
-__device__ __forceinline__ double interp(const double* Ga /*[NA] contiguous*/, const double* u, int ustride) {
-    double s = 0.0;
-#pragma unroll 4
-    for (int a = 0; a < NA; ++a) s += Ga[a] * u[a * ustride];
-    return s;
-}
-
+//             the residual r[a][dp] = sum_q sum_slot G[q][slot][a] R[q][dp][slot] (_Res_Basic) rides in the same q loop
+//   phase D   element matrix -> shared memory in (node pair, block entry) order -> red.global.add.f64 with the NV*NV
+//             entries of a node pair on adjacent lanes (72 contiguous bytes for NV = 3: ~3 L2 sectors per pair, not 9).
 template <class F>
 struct Smem {
     static constexpr int MROWS = F::NA * F::NV * F::NV;
-    static constexpr int ND1 = F::ND > 0 ? F::ND : 1;
-    static constexpr int NWT = F::NW + F::NCW, NWT1 = NWT > 0 ? NWT : 1;
-    static constexpr int KS1 = F::KS > 0 ? F::KS : 1;
-    static constexpr int KLD = F::NA + 1 + (F::NA & 1);   // odd leading dimension: conflict-free strided reads in phase C3
     static constexpr int NAP = F::NA + (F::NA & 1);        // G rows padded to an even length (16 B aligned rows)
     static constexpr int DPB = F::NSD * F::NV * F::KS;     // tangent entries per dual variable dp ...
     static constexpr int DPS = DPB + (DPB & 1);            // ... padded to an even stride
     static constexpr int NDS = F::ND > 0 ? F::NV * DPS : 1;
+    static constexpr int NVLI = F::LINEAR ? 0 : F::L1 * F::NV;   // field components interpolated: unknowns at every level ...
+    static constexpr int NVL = NVLI + F::NC;                     // ... then the CONTROLPOINT_VAR fields
     struct alignas(16) GD {
         double G[F::NQ][4][NAP];
         double D[F::NQ][NDS];                      // D[q][dp][(dsi*NV + bp)*KS + ks], dp stride DPS
@@ -143,15 +135,15 @@ struct Smem {
         double I[F::NQ][9];                        // Jacobian, then its inverse
         double wgt[F::NQ];
         double nrm[F::NQ][3];
-        double w[F::NQ][NWT1];
+        double gu[F::NQ][NVL > 0 ? NVL : 1][4];    // value and reference gradient of every field component
     };
     union {
         GD gd;
-        double Ke[F::HAS_K ? MROWS : 1][KLD];      // phase C3 staging (G and D are dead by then)
+        double Ke[F::HAS_K ? MROWS * F::NA : 1];   // phase D staging, (node pair, block entry) order (G and D are dead by then)
     };
     union {
-        Geo geo;                                   // phases B1..B5
-        int em[F::HAS_K ? F::NA * F::NA : 1];      // phase C: node pair -> block-CSR entry of this element
+        Geo geo;                                   // phases B1..B3
+        int em[F::HAS_K ? F::NA * F::NA : 1];      // phases C, D: node pair -> block-CSR entry of this element
     };
     double R[F::NQ][F::NV * 4];
     double xe[F::NA][3];
@@ -167,7 +159,8 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
     static_assert(sizeof(Smem<F>) <= F::SMEM, "emitter under-estimated the shared-memory footprint");
     const int tid = threadIdx.x;
     constexpr int NA = F::NA, NQ = F::NQ, NV = F::NV, BB = NV * NV, MROWS = NA * NV * NV, TPB = F::TPB;
-    constexpr int NWT = F::NW + F::NCW;
+    constexpr int NVLI = Smem<F>::NVLI, NVL = Smem<F>::NVL;
+    static_assert(TPB >= 64 && TPB % 32 == 0, "the block needs one point-function warp and at least one geometry warp");
 
     for (long long item = blockIdx.x; item < A.n_items; item += gridDim.x) {
         long long e = item;
@@ -197,15 +190,40 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
             int a = i % NA, c = i / NA;
             S.ce[c][a] = A.cpv[c][A.conn[e * NA + a]];
         }
-        __syncthreads();
-        // ---- phase B1: Jacobian J[q][i][X] = dx_i/dX -----------------------------------------
-        for (int o = tid; o < NQ * 9; o += TPB) {
-            const int q = o / 9, r = o - q * 9, i = r / 3, X = r - i * 3;
-            const double* dN = ref + ((1 + X) * NQ + q) * NA;
-            double s = 0.0;
+        constexpr int NEM = F::HAS_K ? (NA * NA + TPB - 1) / TPB : 1;
+        int emr[NEM];                                   // scatter map of this element: in flight during phase B
+        if constexpr (F::HAS_K) {
+            const int* em = A.emap + e * (NA * NA);
 #pragma unroll
-            for (int a = 0; a < NA; ++a) s += dN[a] * S.xe[a][i];
-            S.geo.I[q][r] = s;
+            for (int k = 0; k < NEM; ++k) emr[k] = tid + k * TPB < NA * NA ? em[tid + k * TPB] : 0;
+        }
+        __syncthreads();
+        // ---- phase B1: Jacobian and reference gradients of every field, one pass over the tables ----
+        for (int o = tid; o < NQ * 4; o += TPB) {
+            const int q = o >> 2, X = o & 3;            // X = 0: shape functions, 1..3: d/dX
+            const double* dN = ref + (X * NQ + q) * NA;
+            double j0 = 0.0, j1 = 0.0, j2 = 0.0;
+            double acc[NVL > 0 ? NVL : 1];
+#pragma unroll
+            for (int v = 0; v < NVL; ++v) acc[v] = 0.0;
+#pragma unroll
+            for (int a = 0; a < NA; ++a) {
+                const double d = dN[a];
+                j0 += d * S.xe[a][0];
+                j1 += d * S.xe[a][1];
+                j2 += d * S.xe[a][2];
+#pragma unroll
+                for (int v = 0; v < NVLI; ++v) acc[v] += d * S.ue[v / NV][a][v % NV];
+#pragma unroll
+                for (int c = 0; c < F::NC; ++c) acc[NVLI + c] += d * S.ce[c][a];
+            }
+            if (X > 0) {
+                S.geo.I[q][0 * 3 + X - 1] = j0;
+                S.geo.I[q][1 * 3 + X - 1] = j1;
+                S.geo.I[q][2 * 3 + X - 1] = j2;
+            }
+#pragma unroll
+            for (int v = 0; v < NVL; ++v) S.geo.gu[q][v][X] = acc[v];
         }
         __syncthreads();
         // ---- phase B2: inverse, weight, normal -----------------------------------------------
@@ -242,102 +260,70 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
             S.geo.nrm[q][0] = nrm[0]; S.geo.nrm[q][1] = nrm[1]; S.geo.nrm[q][2] = nrm[2];
         }
         __syncthreads();
-        // ---- phase B3: physical gradients ----------------------------------------------------
-        for (int o = tid; o < NQ * NA; o += TPB) {
-            const int q = o / NA, a = o - q * NA;
-            const double d0 = ref[(1 * NQ + q) * NA + a], d1 = ref[(2 * NQ + q) * NA + a], d2 = ref[(3 * NQ + q) * NA + a];
-            const double* I = S.geo.I[q];
-            S.gd.G[q][0][a] = ref[(0 * NQ + q) * NA + a];
+        // ---- phase B3: warp 0 evaluates the point function, the other warps the physical gradients ----
+        if (tid < 32) {
+            for (int q = tid; q < NQ; q += 32) {
+                const double* I = S.geo.I[q];
+                double w[F::NW > 0 ? F::NW : 1], c[F::NCW > 0 ? F::NCW : 1];
 #pragma unroll
-            for (int s = 0; s < 3; ++s) S.gd.G[q][1 + s][a] = (d0 * I[0 * 3 + s] + d1 * I[1 * 3 + s]) + d2 * I[2 * 3 + s];
-        }
-        __syncthreads();
-        // ---- phase B4: words at quadrature points (_Var_Basic) --------------------------------
-        if constexpr (NWT > 0) {
-            for (int o = tid; o < NQ * NWT; o += TPB) {
-                const int q = o / NWT, k = o - q * NWT;
-                double v;
-                if (k < F::NW) v = interp<NA>(&S.gd.G[q][F::wslot(k)][0], &S.ue[F::wlev(k)][0][F::wpos(k)], NV);
-                else v = interp<NA>(&S.gd.G[q][F::cslot(k - F::NW)][0], &S.ce[F::cfield(k - F::NW)][0], 1);
-                S.geo.w[q][k] = v;
-            }
-            __syncthreads();
-        }
-        if constexpr (F::EVAL) {
-            // ---- argument arrays of the quadrature-point callback; nothing else to do for this item ----
-            const size_t qbase = (size_t)A.elem_ref[e] * NQ;
-            for (int q = tid; q < NQ; q += TPB) {
-                double w[F::NW > 0 ? F::NW : 1], c[F::NCW > 0 ? F::NCW : 1], out[F::NQPO > 0 ? F::NQPO : 1];
-#pragma unroll
-                for (int k = 0; k < F::NW; ++k) w[k] = S.geo.w[q][k];
-#pragma unroll
-                for (int k = 0; k < F::NCW; ++k) c[k] = S.geo.w[q][F::NW + k];
-                F::qp_eval(w, c, A, out);
-#pragma unroll
-                for (int k = 0; k < F::NQPO; ++k) A.qpo[k][qbase + q] = out[k];
-            }
-            continue;
-        }
-        // ---- phase B5: point function ----------------------------------------------------------
-        for (int q = tid; q < NQ; q += TPB) {
-            double w[F::NW > 0 ? F::NW : 1], c[F::NCW > 0 ? F::NCW : 1];
-#pragma unroll
-            for (int k = 0; k < F::NW; ++k) w[k] = S.geo.w[q][k];
-#pragma unroll
-            for (int k = 0; k < F::NCW; ++k) c[k] = S.geo.w[q][F::NW + k];
-            const double wgt = S.geo.wgt[q];
-            const double nrm[3] = {S.geo.nrm[q][0], S.geo.nrm[q][1], S.geo.nrm[q][2]};
-            double qv[F::NQPI > 0 ? F::NQPI : 1];
-            if constexpr (F::NQPI > 0) {
-                const size_t qbase = (size_t)A.elem_ref[e] * NQ;
-#pragma unroll
-                for (int k = 0; k < F::NQPI; ++k) qv[k] = A.qpi[k][qbase + q];
-            }
-            double R[NV * 4], D[F::ND > 0 ? F::ND : 1];
-#pragma unroll
-            for (int k = 0; k < NV * 4; ++k) R[k] = 0.0;
-#pragma unroll
-            for (int k = 0; k < F::ND; ++k) D[k] = 0.0;
-            F::point(w, c, nrm, qv, A, R, D);
-#pragma unroll
-            for (int k = 0; k < NV * 4; ++k) S.R[q][k] = R[k] * wgt;
-            if constexpr (F::ND > 0) {
-                constexpr int DPB = Smem<F>::DPB, DPS = Smem<F>::DPS;
-#pragma unroll
-                for (int k = 0; k < F::ND; ++k) S.gd.D[q][(k / DPB) * DPS + (k % DPB)] = D[k] * wgt;
-            }
-        }
-        __syncthreads();   // geo is dead from here on: its storage becomes em
-        constexpr int NEM = F::HAS_K ? (NA * NA + TPB - 1) / TPB : 1;
-        int emr[NEM];
-        if constexpr (F::HAS_K) {
-            const int* em = A.emap + e * (NA * NA);
-#pragma unroll
-            for (int k = 0; k < NEM; ++k) emr[k] = tid + k * TPB < NA * NA ? em[tid + k * TPB] : 0;   // in flight during C1
-        }
-        // ---- phase C1: residual ------------------------------------------------------------
-        if constexpr (F::HAS_RES) {
-            constexpr int QS = (TPB / (NA * NV)) < 1 ? 1 : ((TPB / (NA * NV)) > 4 ? 4 : (TPB / (NA * NV)));   // q-range split
-            constexpr int QCH = (NQ + QS - 1) / QS;
-            for (int i = tid; i < NA * NV * QS; i += TPB) {
-                const int part = i / (NA * NV), j = i - part * (NA * NV);
-                const int v = j % NV, a = j / NV;
-                const int q1 = (part + 1) * QCH < NQ ? (part + 1) * QCH : NQ;
-                double s = 0.0;
-                for (int q = part * QCH; q < q1; ++q) {
-#pragma unroll
-                    for (int sl = 0; sl < 4; ++sl) s += S.gd.G[q][sl][a] * S.R[q][v * 4 + sl];
+                for (int k = 0; k < F::NW + F::NCW; ++k) {
+                    const int slot = k < F::NW ? F::wslot(k) : F::cslot(k - F::NW);
+                    const int var = k < F::NW ? F::wlev(k) * NV + F::wpos(k) : NVLI + F::cfield(k - F::NW);
+                    const double* gu = S.geo.gu[q][var];
+                    const double v = slot == 0 ? gu[0]
+                                               : (gu[1] * I[0 * 3 + slot - 1] + gu[2] * I[1 * 3 + slot - 1]) + gu[3] * I[2 * 3 + slot - 1];
+                    if (k < F::NW) w[k] = v; else c[k - F::NW] = v;
                 }
-                if (s != 0.0) red_add(A.res + (size_t)S.node[a] * NV + v, s);
+                if constexpr (F::EVAL) {
+                    // argument arrays of the quadrature-point callback (phase A of the two-phase update)
+                    double out[F::NQPO > 0 ? F::NQPO : 1];
+                    F::qp_eval(w, c, A, out);
+                    const size_t qbase = (size_t)A.elem_ref[e] * NQ;
+#pragma unroll
+                    for (int k = 0; k < F::NQPO; ++k) A.qpo[k][qbase + q] = out[k];
+                } else {
+                    const double wgt = S.geo.wgt[q];
+                    const double nrm[3] = {S.geo.nrm[q][0], S.geo.nrm[q][1], S.geo.nrm[q][2]};
+                    double qv[F::NQPI > 0 ? F::NQPI : 1];
+                    if constexpr (F::NQPI > 0) {
+                        const size_t qbase = (size_t)A.elem_ref[e] * NQ;
+#pragma unroll
+                        for (int k = 0; k < F::NQPI; ++k) qv[k] = A.qpi[k][qbase + q];
+                    }
+                    double R[NV * 4], D[F::ND > 0 ? F::ND : 1];
+#pragma unroll
+                    for (int k = 0; k < NV * 4; ++k) R[k] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < F::ND; ++k) D[k] = 0.0;
+                    F::point(w, c, nrm, qv, A, R, D);
+#pragma unroll
+                    for (int k = 0; k < NV * 4; ++k) S.R[q][k] = R[k] * wgt;
+                    if constexpr (F::ND > 0) {
+                        constexpr int DPB = Smem<F>::DPB, DPS = Smem<F>::DPS;
+#pragma unroll
+                        for (int k = 0; k < F::ND; ++k) S.gd.D[q][(k / DPB) * DPS + (k % DPB)] = D[k] * wgt;
+                    }
+                }
+            }
+        } else if (!F::EVAL) {
+            for (int o = tid - 32; o < NQ * NA; o += TPB - 32) {
+                const int q = o / NA, a = o - q * NA;
+                const double d0 = ref[(1 * NQ + q) * NA + a], d1 = ref[(2 * NQ + q) * NA + a], d2 = ref[(3 * NQ + q) * NA + a];
+                const double* I = S.geo.I[q];
+                S.gd.G[q][0][a] = ref[(0 * NQ + q) * NA + a];
+#pragma unroll
+                for (int s = 0; s < 3; ++s) S.gd.G[q][1 + s][a] = (d0 * I[0 * 3 + s] + d1 * I[1 * 3 + s]) + d2 * I[2 * 3 + s];
             }
         }
-        // ---- phase C2: tangent ---------------------------------------------------------------
+        if constexpr (F::EVAL) continue;
+        __syncthreads();   // geo is dead from here on: its storage becomes em
+        // ---- phase C: tangent (+ residual) ----------------------------------------------------
         if constexpr (F::HAS_K) {
 #pragma unroll
             for (int k = 0; k < NEM; ++k)
                 if (tid + k * TPB < NA * NA) S.em[tid + k * TPB] = emr[k];
             constexpr int NTC = F::NTC, KS = F::KS, NSD = F::NSD, CG = F::CG, LPW = F::LPW, NPAIR = NA * NV;
-            constexpr int DPB = Smem<F>::DPB, DPS = Smem<F>::DPS;
+            constexpr int DPS = Smem<F>::DPS;
             static_assert(NTC % 2 == 0 && CG * NTC >= NA && LPW <= 32 && F::W * LPW >= NPAIR * CG && F::W * 32 <= TPB, "bad tangent tiling");
             const int lane = tid & 31, warp = tid >> 5;
             const int t = warp * LPW + lane;                         // tile index: column group major, then dp, then node
@@ -350,13 +336,19 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
             for (int r = 0; r < NV; ++r)
 #pragma unroll
                 for (int c = 0; c < NTC; ++c) acc[r][c] = 0.0;
+            double racc = 0.0;
             if (tile_on) {
 #pragma unroll 1
                 for (int q = 0; q < NQ; ++q) {
                     // stage 1 (registers): T[bp][ks] = sum_d G[q][dslot(d)][a] * D[q][dp][d][bp][ks]
-                    double g[NSD > 0 ? NSD : 1];
+                    double g4[4];
 #pragma unroll
-                    for (int d = 0; d < NSD; ++d) g[d] = S.gd.G[q][F::dslot(d)][a];
+                    for (int sl = 0; sl < 4; ++sl) g4[sl] = S.gd.G[q][sl][a];
+                    if (F::HAS_RES && cgi == 0) {
+                        const double2 r01 = *reinterpret_cast<const double2*>(&S.R[q][dp * 4]);
+                        const double2 r23 = *reinterpret_cast<const double2*>(&S.R[q][dp * 4 + 2]);
+                        racc += (g4[0] * r01.x + g4[1] * r01.y) + (g4[2] * r23.x + g4[3] * r23.y);
+                    }
                     double dv[DPS];
                     const double2* Dq = reinterpret_cast<const double2*>(&S.gd.D[q][dp * DPS]);
 #pragma unroll
@@ -371,7 +363,7 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
                         for (int ks = 0; ks < KS; ++ks) {
                             double tv = 0.0;
 #pragma unroll
-                            for (int d = 0; d < NSD; ++d) tv += g[d] * dv[(d * NV + bp) * KS + ks];
+                            for (int d = 0; d < NSD; ++d) tv += g4[F::dslot(d)] * dv[(d * NV + bp) * KS + ks];
                             T[bp][ks] = tv;
                         }
                     // stage 2: rank-KS update of the lane's NV x NTC tile
@@ -389,23 +381,44 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
                         }
                     }
                 }
+                if (F::HAS_RES && cgi == 0 && racc != 0.0) red_add(A.res + (size_t)S.node[a] * NV + dp, racc);
             }
             __syncthreads();        // every warp is done with G, D and R: their storage becomes Ke
-            // ---- phase C3: stage the element matrix, then scatter with node-pair blocks on adjacent lanes ----
+            // ---- phase D: stage the element matrix, then scatter with node-pair blocks on adjacent lanes ----
             if (tile_on) {
 #pragma unroll
-                for (int bp = 0; bp < NV; ++bp)
+                for (int c = 0; c < NTC; ++c)
+                    if (b0 + c < NA) {
 #pragma unroll
-                    for (int c = 0; c < NTC; ++c)
-                        if (b0 + c < NA) S.Ke[a * BB + dp * NV + bp][b0 + c] = acc[bp][c];
+                        for (int bp = 0; bp < NV; ++bp) S.Ke[(a * NA + b0 + c) * BB + dp * NV + bp] = acc[bp][c];
+                    }
             }
             __syncthreads();
+            {
+                constexpr int DK = TPB % BB, DPAIR = TPB / BB;      // entry i = pair*BB + k advances by TPB per step
+                int pr = tid / BB, k = tid - pr * BB;
 #pragma unroll 4
-            for (int i = tid; i < MROWS * NA; i += TPB) {
-                const int p = i / BB, k = i - p * BB;          // node pair p = a*NA + b, entry k = dp*NV + bp of its block
-                const int a = p / NA, b = p - a * NA;
-                const double v = S.Ke[a * BB + k][b];
-                if (v != 0.0) red_add(A.Kval + (size_t)S.em[p] * BB + k, v);
+                for (int i = tid; i < MROWS * NA; i += TPB) {
+                    const double v = S.Ke[i];
+                    if (v != 0.0) red_add(A.Kval + (size_t)S.em[pr] * BB + k, v);
+                    k += DK; pr += DPAIR;
+                    if (k >= BB) { k -= BB; ++pr; }
+                }
+            }
+        } else if constexpr (F::HAS_RES) {
+            // residual-only kernels (_Res_Basic)
+            constexpr int QS = (TPB / (NA * NV)) < 1 ? 1 : ((TPB / (NA * NV)) > 4 ? 4 : (TPB / (NA * NV)));   // q-range split
+            constexpr int QCH = (NQ + QS - 1) / QS;
+            for (int i = tid; i < NA * NV * QS; i += TPB) {
+                const int part = i / (NA * NV), j = i - part * (NA * NV);
+                const int v = j % NV, a = j / NV;
+                const int q1 = (part + 1) * QCH < NQ ? (part + 1) * QCH : NQ;
+                double s = 0.0;
+                for (int q = part * QCH; q < q1; ++q) {
+#pragma unroll
+                    for (int sl = 0; sl < 4; ++sl) s += S.gd.G[q][sl][a] * S.R[q][v * 4 + sl];
+                }
+                if (s != 0.0) red_add(A.res + (size_t)S.node[a] * NV + v, s);
             }
         }
     }

@@ -132,8 +132,9 @@ def _form(name, spec, blk, n_a, n_q, linear, evalk=False):
     dpb = nsd * nv * ks
     nds = nv * (dpb + (dpb & 1)) if nd else 1
     gd = _align16(8 * (n_q * 4 * nap + n_q * nds))
-    ke = 8 * (mrows if terms else 1) * (nap + 1)
-    geo = _align16(max(8 * n_q * (9 + 1 + 3 + max(len(inner) + len(cpw), 1)), 4 * n_a * n_a if terms else 4))
+    ke = 8 * (mrows * n_a if terms else 1)
+    nvl = (0 if linear else L1 * nv) + len(fields)
+    geo = _align16(max(8 * n_q * (9 + 1 + 3 + 4 * max(nvl, 1)), 4 * n_a * n_a if terms else 4))
     smem = _align16(max(gd, ke)) + geo + 8 * (n_q * nv * 4 + n_a * 3 + L1 * n_a * nv
                                              + max(len(fields), 1) * n_a) + 4 * n_a + 32
     body = "\n".join(lines).replace("@SMEM@", str(smem))

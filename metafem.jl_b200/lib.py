@@ -49,6 +49,7 @@ _SIGS = {
     "mfb_set_stream": (C.c_int, [_P, _P]),
     "mfb_launch_count": (C.c_int64, [_P]),
     "mfb_synchronize": (C.c_int, [_P]),
+    "mfb_measure_fp64_peak": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "mfb_profile_enable": (C.c_int, [_P, C.c_int]),
     "mfb_profile_get": (C.c_int, [_P, _P, _P]),
     "mfb_mesh_set": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, C.c_int, _P, _P, _P, _P, _P, _P]),
