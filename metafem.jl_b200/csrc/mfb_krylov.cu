@@ -21,7 +21,7 @@
 namespace {
 
 constexpr int TPB = 256;
-constexpr int MAXT = 48;   // max terms of one fused vector update
+constexpr int MAXT = 64;   // max terms of one fused vector update
 constexpr int MAXD = 24;   // max dots of one fused reduction
 constexpr int RED_BLOCKS = 1184;  // 8 x 148 SMs, 256 threads each
 

@@ -1,0 +1,89 @@
+"""The reference's own example inputs on the CUDA path, against the reference's own published outputs (tests/golden/*.npz,
+made by tests/golden/make_golden.py from /root/reference/examples): unstructured tet10 and hex20 meshes, hash-ordered
+mid-edge nodes, the solver and tolerance the example scripts use. The oracle only builds the mesh tables here (the front
+end's job); assembly, pattern and solve run through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+from scipy.spatial import cKDTree
+
+from helpers import product_from_oracle
+from oracle import refgeom as rg, femmesh as fm, assembly as oasm
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _match(mesh_x, pts, scale=1.0):
+    dist, idx = cKDTree(mesh_x.T * scale).query(pts.astype(np.float64))
+    assert len(np.unique(idx)) == len(idx)
+    return dist, idx
+
+
+def test_thermal_conduction_3d_cuda_matches_reference_result(built_lib):
+    """examples/thermal_conduction/3D_Script.jl -> 3D_MetaFEM_Result.vtk (15 334 tet10, convection BC, idrs! s=8, tol 1e-6)."""
+    import metafem_b200 as m
+    from metafem_jl_b200.frontend import weakform as wf
+    g = np.load(os.path.join(GOLD, "thermal3d.npz"))
+    tm = rg.construct_TotalMesh_3D(g["vert"] / 100, g["conn"])
+    mesh = fm.mesh_Classical(tm, [rg.get_BoundaryMesh(tm)], "SIMPLEX")
+    fm.update_Mesh(mesh)
+    dom = oasm.Domain(mesh, wf.thermal_conduction())
+    dom.cp["T"][:] = 273.15 + 20
+    dom.cp["s"][:] = 1600.0
+    dom.globalfield.converge_tol = 1e-6
+    fd = product_from_oracle(dom)
+    try:
+        m.assemble_Global_Variables(fd)
+        m.compile_Updater_GPU(1, fd)
+        fd.linear_solver = lambda d: m.iterative_Solve(d, Sv_func="idrs!", maxiter=2000, max_pass=10, s=8)
+        hist = m.update_OneStep(fd.time_discretization, fem_domain=fd)
+        assert hist[-1] < 1e-6, hist
+        m.dessemble_X(fd)
+        T = fd.controlpoints["T"]
+    finally:
+        fd.close()
+    dist, idx = _match(mesh.x, g["points"], 100.0)
+    assert dist.max() < 1e-4
+    T, Tg = T[idx], g["T"]
+    assert np.abs(T - Tg).max() < 1e-2                       # both are iterative solutions at residual tolerance 1e-6
+    assert np.linalg.norm(T - Tg) / np.linalg.norm(Tg - 293.15) < 2e-3
+
+
+def test_stress_concentration_3d_cuda_matches_reference_result(built_lib):
+    """examples/linear_elasticity/stress_concentration/3D_Script.jl -> 3D_MetaFEM.vtk (3 375 hex20, penalty BCs, traction)."""
+    import metafem_b200 as m
+    from metafem_jl_b200.frontend import weakform as wf
+    g = np.load(os.path.join(GOLD, "stress3d.npz"))
+    tm = rg.construct_TotalMesh_3D(g["vert"], g["conn"])
+    fids = rg.get_BoundaryMesh(tm)
+    cen = rg.face_centroids(tm, fids)
+    Lb, err = 5.0, 0.05
+    sel = lambda d, v: fids[(cen[d] < v + err) & (cen[d] > v - err)]
+    groups = [sel(0, 0), sel(1, 0), sel(2, 0), np.concatenate([sel(0, Lb), sel(2, Lb)]), sel(1, Lb)]
+    mesh = fm.mesh_Classical(tm, groups, "CUBE")
+    fm.update_Mesh(mesh)
+    E, nu = 210e9, 0.3
+    lam, mu = E * nu / ((1 + nu) * (1 - 2 * nu)), E / (2 * (1 + nu))
+    spec = wf.linear_elasticity(lam, mu, 10000 * E / Lb ** 2, fixed_bg={1: 1, 2: 2, 3: 3},
+                                traction_bgs=((5, ("sl", {(2, 2)})),))
+    dom = oasm.Domain(mesh, spec)
+    dom.cp["sl2"][:] = 1.0
+    dom.globalfield.converge_tol = 1e-8
+    fd = product_from_oracle(dom)
+    try:
+        m.assemble_Global_Variables(fd)
+        m.compile_Updater_GPU(1, fd)
+        fd.linear_solver = lambda d: m.iterative_Solve(d, Sv_func="idrs!", maxiter=2000, max_pass=20, s=20)
+        hist = m.update_OneStep(fd.time_discretization, fem_domain=fd)
+        assert hist[-1] < 1e-8, hist
+        m.dessemble_X(fd)
+        d = {k: fd.controlpoints[k].copy() for k in ("d1", "d2", "d3")}
+    finally:
+        fd.close()
+    dist, idx = _match(mesh.x, g["points"])
+    assert dist.max() < 1e-5
+    for k in ("d1", "d2", "d3"):
+        a, b = d[k][idx], g[k]
+        assert np.linalg.norm(a - b) / np.linalg.norm(b) < 1e-4, k
