@@ -336,6 +336,7 @@ def main():
         "newton_step_ms": ms_step, "assembly_ms": asm_ms, "assembly_dof_per_s": ndof_global / (asm_ms * 1e-3),
         "element_kernel_ms": elem_ms, "solve_ms": pms[3] / max(pcnt[3], 1), "spmv_ms": spmv_ms,
         "spmv_share_of_step": pms[0] / ms_total,
+        "halo_exchange_ms_per_step": pms[5] / K, "krylov_reductions_ms_per_step": pms[6] / K,
         "roofline": {"bound": "hbm", "kernel": "k_spmv_bsr<3>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
                      "algorithmic_bytes": spmv_bytes, "launches_timed": int(pcnt[0]), "avg_ms": spmv_ms},

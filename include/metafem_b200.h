@@ -68,7 +68,8 @@ int mfb_set_stream(mfb_ctx *ctx, void *cuda_stream);
 int64_t mfb_launch_count(mfb_ctx *ctx);
 int mfb_synchronize(mfb_ctx *ctx);
 /* CUDA-event timers on the context's stream. ids: 0 SpMV, 1 K_nonlinear_func, 2 K_linear_func,
- * 3 Krylov solve, 4 domain element kernel, 7 boundary element kernels. mfb_profile_get sums and
+ * 3 Krylov solve, 4 domain element kernel, 5 interface exchange-add (multi-GPU), 6 Krylov reductions (+ allreduce),
+ * 7 boundary element kernels. mfb_profile_get sums and
  * clears them: ms[8], count[8]. */
 /* Measured FP64 FMA throughput of the device in TFLOP/s (register-resident FMA chains on every SM): the peak the
  * FP64-bound element kernels are reported against. */

@@ -16,6 +16,7 @@
 #include <thrust/sort.h>
 #include <thrust/unique.h>
 
+#include <algorithm>
 #include <cstring>
 
 #include "mfb_internal.h"
@@ -86,6 +87,22 @@ __global__ void k_merge_low(double* v, const double* low, const int* slots, int6
     size_t i = (size_t)slots[t / nv] * nv + t % nv;
     v[i] = low[i] + v[i];
 }
+// One pass over the union of shared nodes: v[node] = sum over the sharing ranks in ascending rank order, this rank's own
+// value in its place (contributions of lower ranks first, then own, then higher ranks) -- every rank holding the node
+// performs the additions in the same order, so all copies stay bit-identical.
+__global__ void k_halo_merge(double* v, const int* uni, const int* uptr, const int* uidx, const int* ulow, int64_t n_union,
+                             int nv, const double* recv) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_union * nv) return;
+    const int u = (int)(t / nv), k = (int)(t % nv);
+    const int lo = uptr[u], hi = uptr[u + 1], nlow = ulow[u];
+    const size_t at = (size_t)uni[u] * nv + k;
+    double s = 0.0;
+    for (int e = lo; e < lo + nlow; ++e) s += recv[(size_t)uidx[e] * nv + k];
+    s = s + v[at];
+    for (int e = lo + nlow; e < hi; ++e) s += recv[(size_t)uidx[e] * nv + k];
+    v[at] = s;
+}
 __global__ void k_map_nodes(const int* ref_ids_1based, const int* perm, int64_t n, int* out) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t < n) out[t] = perm[ref_ids_1based[t] - 1];
@@ -107,6 +124,7 @@ struct Comm {
     std::vector<int64_t> offsets;          // [n_neighbors + 1] into slots
     DevBuf<int> slots;                     // internal node ids, concatenated per neighbour
     DevBuf<int> uni;                       // unique union of slots
+    DevBuf<int> uptr, uidx, ulow;          // per union node: receive-buffer positions (ascending neighbour rank), # from lower ranks
     int64_t n_union = 0;
     DevBuf<double> sendbuf, recvbuf, low;
     int buf_nv = 0;
@@ -157,7 +175,8 @@ void mfb_comm_free(mfb_ctx* ctx) {
     Comm* c = ctx->comm;
     if (!c) return;
     if (c->comm) nccl().CommDestroy(c->comm);
-    c->slots.release(); c->uni.release(); c->sendbuf.release(); c->recvbuf.release(); c->low.release();
+    c->slots.release(); c->uni.release(); c->uptr.release(); c->uidx.release(); c->ulow.release();
+    c->sendbuf.release(); c->recvbuf.release(); c->low.release();
     ctx->owned.release(); ctx->gid.release();
     delete c;
     ctx->comm = nullptr;
@@ -204,6 +223,27 @@ extern "C" int mfb_interface_set(mfb_ctx* ctx, int n_neighbors, const int32_t* n
         thrust::device_ptr<int> up(c->uni.p);
         thrust::sort(pol, up, up + total);
         c->n_union = thrust::unique(pol, up, up + total) - up;
+        // merge lists: for every union node the positions of its copies in the receive buffer, neighbours ascending
+        std::vector<int> hs(total), hu(c->n_union);
+        MFB_CUDA(cudaMemcpyAsync(hs.data(), c->slots.p, total * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        MFB_CUDA(cudaMemcpyAsync(hu.data(), c->uni.p, c->n_union * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+        std::vector<int> uptr(c->n_union + 1, 0), ulow(c->n_union, 0), uidx(total);
+        auto uof = [&](int slot) { return (int)(std::lower_bound(hu.begin(), hu.end(), slot) - hu.begin()); };
+        for (int64_t p = 0; p < total; ++p) uptr[uof(hs[p]) + 1]++;
+        for (int64_t u = 0; u < c->n_union; ++u) uptr[u + 1] += uptr[u];
+        std::vector<int> fill(uptr.begin(), uptr.end() - 1);
+        for (int i = 0; i < n_neighbors; ++i)                      // ascending neighbour rank == ascending position ranges
+            for (int64_t p = c->offsets[i]; p < c->offsets[i + 1]; ++p) {
+                const int u = uof(hs[p]);
+                uidx[fill[u]++] = (int)p;
+                if (c->neighbors[i] < c->rank) ulow[u]++;
+            }
+        MFB_CUDA(c->uptr.alloc(c->n_union + 1)); MFB_CUDA(c->ulow.alloc(c->n_union)); MFB_CUDA(c->uidx.alloc(total));
+        MFB_CUDA(cudaMemcpyAsync(c->uptr.p, uptr.data(), uptr.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        MFB_CUDA(cudaMemcpyAsync(c->ulow.p, ulow.data(), ulow.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        MFB_CUDA(cudaMemcpyAsync(c->uidx.p, uidx.data(), uidx.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        MFB_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     {   // global number of nodes = sum over ranks of owned nodes (normalises every residual norm)
         auto pol = thrust::cuda::par.on(ctx->stream);
@@ -231,6 +271,7 @@ int mfb_halo_add(mfb_ctx* ctx, double* v, int nv) {
     Comm* c = ctx->comm;
     if (!c || !c->comm || c->neighbors.empty()) return MFB_OK;
     NcclApi& api = nccl();
+    ProfScope ps(ctx, MFB_T_HALO);
     const int nn = (int)c->neighbors.size();
     const int64_t total = c->offsets[nn];
     if (c->buf_nv < nv) {
@@ -238,7 +279,6 @@ int mfb_halo_add(mfb_ctx* ctx, double* v, int nv) {
         MFB_CUDA(c->recvbuf.alloc(total * nv));
         c->buf_nv = nv;
     }
-    MFB_CUDA(c->low.alloc((size_t)ctx->N * (nv > ctx->n_var ? nv : ctx->n_var)));
     LAUNCH(k_pack, nblk(total * nv), TPB, v, c->slots.p, total, nv, c->sendbuf.p);
     MFB_NCCL(api.GroupStart());
     for (int i = 0; i < nn; ++i) {
@@ -247,17 +287,7 @@ int mfb_halo_add(mfb_ctx* ctx, double* v, int nv) {
         MFB_NCCL(api.Recv(c->recvbuf.p + off, cnt, ncclDouble, c->neighbors[i], c->comm, ctx->stream));
     }
     MFB_NCCL(api.GroupEnd());
-    LAUNCH(k_zero_slots, nblk(c->n_union * nv), TPB, c->low.p, c->uni.p, c->n_union, nv);
-    for (int i = 0; i < nn && c->neighbors[i] < c->rank; ++i) {
-        const int64_t off = c->offsets[i], cnt = c->offsets[i + 1] - off;
-        LAUNCH(k_add_slots, nblk(cnt * nv), TPB, c->low.p, c->slots.p + off, cnt, nv, c->recvbuf.p + off * nv);
-    }
-    LAUNCH(k_merge_low, nblk(c->n_union * nv), TPB, v, c->low.p, c->uni.p, c->n_union, nv);
-    for (int i = 0; i < nn; ++i) {
-        if (c->neighbors[i] < c->rank) continue;
-        const int64_t off = c->offsets[i], cnt = c->offsets[i + 1] - off;
-        LAUNCH(k_add_slots, nblk(cnt * nv), TPB, v, c->slots.p + off, cnt, nv, c->recvbuf.p + off * nv);
-    }
+    LAUNCH(k_halo_merge, nblk(c->n_union * nv), TPB, v, c->uni.p, c->uptr.p, c->uidx.p, c->ulow.p, c->n_union, nv, c->recvbuf.p);
     MFB_CUDA(cudaGetLastError());
     return MFB_OK;
 }

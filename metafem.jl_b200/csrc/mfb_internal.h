@@ -67,7 +67,8 @@ struct BoundaryGroup {
 struct Comm;  // mfb_dist.cu
 
 // CUDA-event timers on the context's stream (bench.py roofline numbers); ids = MFB_T_*
-enum { MFB_T_SPMV = 0, MFB_T_ASM_NONLINEAR = 1, MFB_T_ASM_LINEAR = 2, MFB_T_SOLVE = 3, MFB_T_ELEM_KERNEL = 4, MFB_T_COUNT = 8 };
+enum { MFB_T_SPMV = 0, MFB_T_ASM_NONLINEAR = 1, MFB_T_ASM_LINEAR = 2, MFB_T_SOLVE = 3, MFB_T_ELEM_KERNEL = 4, MFB_T_HALO = 5,
+       MFB_T_REDUCE = 6, MFB_T_COUNT = 8 };
 struct ProfEvents {
     std::vector<cudaEvent_t> start, stop;
 };

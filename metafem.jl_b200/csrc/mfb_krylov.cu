@@ -534,6 +534,7 @@ struct Solver {
     }
     // same reduction, results stay on the device in ctx->scal[0..k) (no host synchronisation)
     int dots_dev(int k, const double* const* xs, const double* const* ys) {
+        ProfScope ps(ctx, MFB_T_REDUCE);
         MultiDot M;
         M.n = k;
         for (int i = 0; i < k; ++i) { M.x[i] = xs[i]; M.y[i] = ys[i]; }
