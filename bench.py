@@ -36,6 +36,8 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--assembly-only", action="store_true", help="development aid: skip the Krylov solve in every step "
                                                                 "(prints timings of the assembly only; never a bench value)")
+    p.add_argument("--spmv-sweep", action="store_true", help="development aid: time the SpMV tuning variants on the assembled "
+                                                             "matrix and exit")
     p.add_argument("--ncu", action="store_true", help="profiler capture run: exactly W warm-up steps, no e2e pass; "
                                                       "numbers printed by such a run are never bench values")
     return p.parse_args()
@@ -284,6 +286,17 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    if args.spmv_sweep:
+        step(False) if args.assembly_only else (fd.ctx.call("mfb_update_x_star", L.ptr(alpha), len(alpha)),
+                                                fd.ctx.call("mfb_assemble_nonlinear", L.ptr(kp), len(kp), gf.t, gf.dt))
+        out = {}
+        for rnd in range(2):
+            for v in range(10):
+                ms = C.c_double(0.0)
+                fd.ctx.call("mfb_spmv_variant_bench", v, 20, C.byref(ms))
+                out.setdefault(v, []).append(round(ms.value, 4))
+        print(json.dumps({"spmv_sweep_ms": out}))
+        return
     if not args.ncu:
         W = max(W, 3)
     with torch.cuda.stream(stream):

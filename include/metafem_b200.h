@@ -205,6 +205,9 @@ int mfb_j2_update_states(mfb_ctx *ctx, const char *prefix);
  * y = K * x in reference numbering (mul!, src/misc/04_GPU_Utils.jl:131). */
 int mfb_spmv(mfb_ctx *ctx, int which_matrix, const double *x, double *y, int64_t n);
 
+/* Development aid: ms per launch of one tuning variant of the 3-variable block SpMV on K_total (0 = production kernel). */
+int mfb_spmv_variant_bench(mfb_ctx *ctx, int variant, int reps, double *ms_per_launch);
+
 typedef struct {
     int32_t passes;        /* restart passes used */
     int32_t iterations;    /* Krylov iterations summed over passes */

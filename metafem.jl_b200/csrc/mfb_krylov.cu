@@ -40,19 +40,18 @@ inline unsigned nblk(int64_t n) { return (unsigned)((n + TPB - 1) / TPB); }
 constexpr int SPMV_ROWS = 64;
 template <int NV> struct SpmvUnroll { static constexpr int value = NV == 1 ? 2 : NV == 2 ? 3 : NV == 3 ? 5 : NV == 4 ? 6 : 8; };
 
-template <int NV>
-__global__ void __launch_bounds__(256) k_spmv_bsr(const int* __restrict__ nodeptr, const int* __restrict__ nodecol,
-                                                  const double* __restrict__ K, const double* __restrict__ x,
-                                                  double* __restrict__ y, int64_t N) {
+template <int NV, int UNR = SpmvUnroll<NV>::value, int MINB = 0, int ROWS = SPMV_ROWS>
+__global__ void __launch_bounds__(256, MINB) k_spmv_bsr(const int* __restrict__ nodeptr, const int* __restrict__ nodecol,
+                                                        const double* __restrict__ K, const double* __restrict__ x,
+                                                        double* __restrict__ y, int64_t N) {
     constexpr int B = NV * NV;
     constexpr int EPW = 32 / B;        // entries per warp step
     constexpr int ACTIVE = EPW * B;    // active lanes (27 of 32 for NV = 3)
-    constexpr int UNR = SpmvUnroll<NV>::value;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int le = lane / B, ik = lane - le * B, i = ik / NV, k = ik - i * NV;
     const double* xk = x + k;
-    const int64_t row0 = blockIdx.x * (int64_t)SPMV_ROWS + warp;
-    const int64_t rend = min((blockIdx.x + 1) * (int64_t)SPMV_ROWS, N);
+    const int64_t row0 = blockIdx.x * (int64_t)ROWS + warp;
+    const int64_t rend = min((blockIdx.x + 1) * (int64_t)ROWS, N);
     if (row0 >= rend) return;
     int ps = nodeptr[row0], pt = nodeptr[row0 + 1];
     for (int64_t row = row0; row < rend; row += 8) {
@@ -1326,6 +1325,50 @@ extern "C" int mfb_krylov_solve_ex(mfb_ctx* ctx, int method, int s, int maxiter,
 extern "C" int mfb_krylov_solve(mfb_ctx* ctx, int method, int s, int maxiter, int max_pass, double tol, uint64_t seed,
                                 double* delta_out, mfb_solve_info* info) {
     return mfb_krylov_solve_ex(ctx, method, s, maxiter, max_pass, tol, seed, MFB_PR_JACOBI, MFB_PL_IDENTITY, 200, delta_out, info);
+}
+
+// Development aid (bench.py --spmv-sweep): times `reps` launches of one (unroll, min-blocks, rows-per-CTA) variant of the
+// NV = 3 block SpMV on K_total with CUDA events; variant 0 is the production kernel. Returns ms per launch.
+extern "C" int mfb_spmv_variant_bench(mfb_ctx* ctx, int variant, int reps, double* ms_out) {
+    if (!ctx || !ms_out) return MFB_ERR_ARG;
+    MFB_REQUIRE(ctx->U > 0 && ctx->n_var == 3, MFB_ERR_STATE, "mfb_spmv_variant_bench: needs a built 3-variable system");
+    MFB_CUDA(cudaSetDevice(ctx->device));
+    const int64_t N = ctx->N, n = N * 3;
+    MFB_TRY(ensure_work(ctx, 2, n));
+    double *x = ctx->work[0].p, *y = ctx->work[1].p;
+    LAUNCH(k_rand, RED_BLOCKS, TPB, x, n, 7ull, 1ull, ctx->gid.p, 3);
+    cudaEvent_t e0, e1;
+    MFB_CUDA(cudaEventCreate(&e0));
+    MFB_CUDA(cudaEventCreate(&e1));
+    const int* np = ctx->nodeptr.p; const int* nc = ctx->nodecol.p; const double* K = ctx->K_total.p;
+    auto launch = [&](int v) {
+        auto g = [&](int rows) { return (unsigned)((N + rows - 1) / rows); };
+        switch (v) {
+            case 0: LAUNCH((k_spmv_bsr<3>), g(64), 256, np, nc, K, x, y, N); break;
+            case 1: LAUNCH((k_spmv_bsr<3, 5, 6, 64>), g(64), 256, np, nc, K, x, y, N); break;
+            case 2: LAUNCH((k_spmv_bsr<3, 4, 6, 64>), g(64), 256, np, nc, K, x, y, N); break;
+            case 3: LAUNCH((k_spmv_bsr<3, 4, 8, 64>), g(64), 256, np, nc, K, x, y, N); break;
+            case 4: LAUNCH((k_spmv_bsr<3, 3, 8, 64>), g(64), 256, np, nc, K, x, y, N); break;
+            case 5: LAUNCH((k_spmv_bsr<3, 6, 5, 64>), g(64), 256, np, nc, K, x, y, N); break;
+            case 6: LAUNCH((k_spmv_bsr<3, 5, 5, 128>), g(128), 256, np, nc, K, x, y, N); break;
+            case 7: LAUNCH((k_spmv_bsr<3, 5, 5, 32>), g(32), 256, np, nc, K, x, y, N); break;
+            case 8: LAUNCH((k_spmv_bsr<3, 4, 6, 128>), g(128), 256, np, nc, K, x, y, N); break;
+            case 9: LAUNCH((k_spmv_bsr<3, 2, 8, 64>), g(64), 256, np, nc, K, x, y, N); break;
+            default: break;
+        }
+    };
+    MFB_REQUIRE(variant >= 0 && variant <= 9, MFB_ERR_ARG, "unknown SpMV variant");
+    for (int i = 0; i < 3; ++i) launch(variant);
+    MFB_CUDA(cudaEventRecord(e0, ctx->stream));
+    for (int i = 0; i < reps; ++i) launch(variant);
+    MFB_CUDA(cudaEventRecord(e1, ctx->stream));
+    MFB_CUDA(cudaEventSynchronize(e1));
+    MFB_CUDA(cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms_out = ms / reps;
+    return MFB_OK;
 }
 
 extern "C" int mfb_spmv(mfb_ctx* ctx, int which, const double* x, double* y, int64_t n) {
