@@ -240,6 +240,16 @@ int mfb_update_dx(mfb_ctx *ctx, const double *beta_params, int n_beta, double si
 int mfb_commit_step(mfb_ctx *ctx);
 int mfb_residue_norm(mfb_ctx *ctx, double *normalized_norm);
 
+/* ---- result hand-off -------------------------------------------------------------------------
+ * dessemble_X! + write_VTK (src/solver/03_GlobalAssembly.jl:63-75, src/mesh/unstructured_mesh/5_VTK.jl:7-157) in one call:
+ * legacy ASCII unstructured grid with the reference's section order. cell_type / el_cp_outer_id are the element type's VTK
+ * id and node permutation (5_VTK.jl:26-118; 1-based local node ids); symbol k is variable sym_var[k] (0-based position in
+ * basic_vars) at time level sym_level[k]; coordinates are (x + shift) * scale, shift = the 3 variables starting at
+ * shift_var (level 0) or none for shift_var < 0. Numbers are printed shortest-round-trip. */
+int mfb_write_vtk(mfb_ctx *ctx, const char *path, int cell_type, int cell_size, const int32_t *el_cp_outer_id,
+                  int n_syms, const char *const *sym_names, const int32_t *sym_var, const int32_t *sym_level,
+                  double scale, int shift_var);
+
 /* ---- multi-GPU: element-block partitioning (new relative to the single-GPU reference, README.md:4) -----------
  * One process per GPU. Each rank calls mfb_mesh_set with ITS block of elements and the nodes they touch (local
  * numbering); matrices/residuals stay unassembled across ranks and the library completes every SpMV result,

@@ -4,4 +4,5 @@ The directory name carries a dot, so it is imported through ``metafem_b200.py`` 
 """
 from . import lib, emitter, api  # noqa: F401
 from .api import (FEM_Domain, GeneralAlpha, GlobalField, MeshTables, assemble_Global_Variables, assemble_X,  # noqa: F401
-                  dessemble_X, compile_Updater_GPU, update_OneStep, iterative_Solve, comm_unique_id, init_distributed)
+                  dessemble_X, compile_Updater_GPU, update_OneStep, iterative_Solve, comm_unique_id, init_distributed,
+                  write_VTK)

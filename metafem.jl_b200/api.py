@@ -279,6 +279,30 @@ def dessemble_X(fem_domain):
         fem_domain.controlpoints[sym][:] = x[sl]
 
 
+# (cell_type, el_cp_outer_id) of write_VTK (5_VTK.jl:26-118), keyed by (dim, n_a): hex20 serendipity, hex8, tet10, tet4
+_VTK_CELLS = {(3, 20): (25, [1, 2, 4, 3, 5, 6, 8, 7, 9, 14, 10, 13, 11, 16, 12, 15, 17, 18, 20, 19]),
+              (3, 8): (12, [1, 2, 4, 3, 5, 6, 8, 7]), (3, 10): (24, [1, 3, 6, 10, 2, 5, 4, 7, 8, 9]), (3, 4): (10, [1, 2, 3, 4])}
+
+
+def write_VTK(fname, fem_domain, scale=1.0, shift_sym=None):
+    """write_VTK(fname, wp; scale, shift_sym) (5_VTK.jl:7-157) straight from the device-resident x (dessemble_X! included):
+    every inner variable at every time level, in the order of the reference's local_innervar_infos naming
+    (d1, d1_t1 -> "d1_t", ...)."""
+    dom = fem_domain
+    spec, n_a = dom.spec, dom.tables.controlpoint_IDs.shape[0]
+    cell_type, outer = _VTK_CELLS[(dom.dim, n_a)]
+    names, var, lev = [], [], []
+    for pos, b in enumerate(spec["basic_vars"]):
+        for td in range(spec["max_time_level"] + 1):
+            names.append(b + ("_" + "t" * td if td else ""))
+            var.append(pos)
+            lev.append(td)
+    shift = -1 if shift_sym is None else spec["basic_vars"].index(f"{shift_sym}1")
+    arr = (C.c_char_p * len(names))(*[s.encode() for s in names])
+    dom.ctx.call("mfb_write_vtk", str(fname).encode(), cell_type, len(outer), L.ptr(_i32(outer)), len(names), arr,
+                 L.ptr(_i32(var)), L.ptr(_i32(lev)), float(scale), shift)
+
+
 def compile_Updater_GPU(domain_ID, fem_domain, tpb=128):
     """compile_Updater_GPU (05_CodeGenerator.jl:265-291): emit CUDA C for every block, compile with NVRTC,
     install K_linear_func / K_nonlinear_func. Returns the generated source (the reference returns the Exprs)."""

@@ -5,7 +5,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmetafem_b200.so")
-SOURCES = ["mfb_api.cu", "mfb_pattern.cu", "mfb_krylov.cu", "mfb_dist.cu", "mfb_qp.cu"]
+SOURCES = ["mfb_api.cu", "mfb_pattern.cu", "mfb_krylov.cu", "mfb_dist.cu", "mfb_qp.cu", "mfb_vtk.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -23,17 +23,19 @@ def _embed_skeleton():
 def build(force=False, verbose=False):
     emb = _embed_skeleton()
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    obj_of = lambda s: os.path.splitext(s)[0] + ".o"
     deps = srcs + [emb, os.path.join(CSRC, "mfb_internal.h"), os.path.join(CSRC, "mfb_skeleton.cuh"),
                    os.path.join(HERE, "..", "include", "metafem_b200.h")]
     objs = []
     for s in srcs:
-        o = s[:-3] + ".o"
+        o = obj_of(s)
         objs.append(o)
-        hdrs = [d for d in deps if not d.endswith(".cu")]
+        hdrs = [d for d in deps if not d.endswith((".cu", ".cpp"))]
         if (not force and os.path.exists(o)
                 and all(os.path.getmtime(o) >= os.path.getmtime(d) for d in [s] + hdrs)):
             continue
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-x", "cu"] if s.endswith(".cpp") else []) + (["-Xptxas", "-v"] if verbose else []) \
+            + ["-c", s, "-o", o]
         subprocess.check_call(cmd)
     if (force or not os.path.exists(LIB) or any(os.path.getmtime(LIB) < os.path.getmtime(o) for o in objs)):
         cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lnvrtc", "-ldl", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]

@@ -85,6 +85,7 @@ _SIGS = {
     "mfb_update_dx": (C.c_int, [_P, _P, C.c_int, C.c_double]),
     "mfb_commit_step": (C.c_int, [_P]),
     "mfb_residue_norm": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "mfb_write_vtk": (C.c_int, [_P, C.c_char_p, C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_char_p), _P, _P, C.c_double, C.c_int]),
     "mfb_comm_unique_id": (C.c_int, [_P]),
     "mfb_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "mfb_interface_set": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),

@@ -21,7 +21,7 @@ def _match(mesh_x, pts, scale=1.0):
     return dist, idx
 
 
-def test_thermal_conduction_3d_cuda_matches_reference_result(built_lib):
+def test_thermal_conduction_3d_cuda_matches_reference_result(built_lib, tmp_path):
     """examples/thermal_conduction/3D_Script.jl -> 3D_MetaFEM_Result.vtk (15 334 tet10, convection BC, idrs! s=8, tol 1e-6)."""
     import metafem_b200 as m
     from metafem_jl_b200.frontend import weakform as wf
@@ -42,10 +42,24 @@ def test_thermal_conduction_3d_cuda_matches_reference_result(built_lib):
         assert hist[-1] < 1e-6, hist
         m.dessemble_X(fd)
         T = fd.controlpoints["T"]
+        # result hand-off: the native write_VTK, same section layout as the reference's file (5_VTK.jl:123-157)
+        out = str(tmp_path / "3D_MetaFEM_Result.vtk")
+        m.write_VTK(out, fd, scale=100.0)
     finally:
         fd.close()
     dist, idx = _match(mesh.x, g["points"], 100.0)
     assert dist.max() < 1e-4
+    from oracle import vtk as ovtk
+    w = ovtk.read_vtk(out)
+    head = open(out).read(200).split("\n")
+    assert head[0] == "# vtk DataFile Version 3.0" and head[2:5] == ["ASCII", "DATASET UNSTRUCTURED_GRID", "POINTS 23703 float"]
+    assert np.array_equal(w["points"], mesh.x.T * 100.0)              # shortest round-trip printing: bit-exact
+    assert np.array_equal(w["T"], T)
+    cells = np.array(w["cells"])
+    assert cells.shape == g["cells"].shape == (15334, 10)
+    # same elements in the same order with the same VTK node permutation: compare through coordinates (the hash-ordered
+    # mid-edge IDs of the reference's run differ for ~8 % of the nodes, their positions do not)
+    assert np.abs(w["points"][cells] - g["points"][g["cells"]]).max() < 1e-4
     T, Tg = T[idx], g["T"]
     assert np.abs(T - Tg).max() < 1e-2                       # both are iterative solutions at residual tolerance 1e-6
     assert np.linalg.norm(T - Tg) / np.linalg.norm(Tg - 293.15) < 2e-3
