@@ -181,6 +181,9 @@ int mfb_export_pattern(mfb_ctx* ctx, int* K_I, int* K_J, int* K_J_ptr, int* K_va
 int mfb_node_ids_init(mfb_ctx* ctx, const unsigned char* owned_ref_dev, const long long* gid_ref_dev);
 int mfb_halo_add(mfb_ctx* ctx, double* v, int nv);
 int mfb_allreduce_sum(mfb_ctx* ctx, double* dev, int n);
+// fused fold of per-block partials + allreduce over peer memory; returns 1 when unavailable (single GPU / NCCL fallback)
+int mfb_reduce_allreduce(mfb_ctx* ctx, const double* partials, int nb, int k, double* out);
+int mfb_p2p_check(mfb_ctx* ctx);
 bool mfb_is_distributed(mfb_ctx* ctx);
 void mfb_comm_free(mfb_ctx* ctx);
 

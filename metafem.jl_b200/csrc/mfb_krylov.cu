@@ -518,6 +518,14 @@ struct Solver {
         MFB_TRY(mfb_halo_add(ctx, y, ctx->n_var));
         return Pl(y);
     }
+    // fold the per-block partials of k reductions into ctx->scal[0..k) and sum them over the ranks
+    int finish(int k) {
+        double* partials = ctx->scal.p + 64;
+        const int rc = mfb_reduce_allreduce(ctx, partials, RED_BLOCKS, k, ctx->scal.p);
+        if (rc != 1) return rc;
+        LAUNCH(k_reduce_partials, k, 256, partials, RED_BLOCKS, ctx->scal.p);
+        return mfb_allreduce_sum(ctx, ctx->scal.p, k);
+    }
     // dots: results in ctx->h_scal[0..k)
     int dots(int k, const double* const* xs, const double* const* ys) {
         MultiDot M;
@@ -525,8 +533,7 @@ struct Solver {
         for (int i = 0; i < k; ++i) { M.x[i] = xs[i]; M.y[i] = ys[i]; }
         double* partials = ctx->scal.p + 64;
         LAUNCH(k_multidot, RED_BLOCKS, TPB, M, n, partials, mask(), ctx->n_var);
-        LAUNCH(k_reduce_partials, k, 256, partials, RED_BLOCKS, ctx->scal.p);
-        MFB_TRY(mfb_allreduce_sum(ctx, ctx->scal.p, k));
+        MFB_TRY(finish(k));
         MFB_CUDA(cudaMemcpyAsync(ctx->h_scal, ctx->scal.p, k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         MFB_CUDA(cudaStreamSynchronize(ctx->stream));
         return MFB_OK;
@@ -539,8 +546,7 @@ struct Solver {
         for (int i = 0; i < k; ++i) { M.x[i] = xs[i]; M.y[i] = ys[i]; }
         double* partials = ctx->scal.p + 64;
         LAUNCH(k_multidot, RED_BLOCKS, TPB, M, n, partials, mask(), ctx->n_var);
-        LAUNCH(k_reduce_partials, k, 256, partials, RED_BLOCKS, ctx->scal.p);
-        return mfb_allreduce_sum(ctx, ctx->scal.p, k);
+        return finish(k);
     }
     // y = ay*y + sum (c_i * *cp_i) x_i with device-resident factors; optional fused ||y||^2 left in ctx->scal[0]
     int lincomb_dev(double* y, double ay, int k, const double* c, const double* const* cp, const double* const* xs,
@@ -550,10 +556,7 @@ struct Solver {
         for (int i = 0; i < k; ++i) { L.c[i] = c[i]; L.cp[i] = cp[i]; L.x[i] = xs[i]; }
         double* partials = norm2 ? ctx->scal.p + 64 : nullptr;
         LAUNCH(k_lincomb, RED_BLOCKS, TPB, L, n, partials, mask(), ctx->n_var);
-        if (norm2) {
-            LAUNCH(k_reduce_partials, 1, 256, partials, RED_BLOCKS, ctx->scal.p);
-            MFB_TRY(mfb_allreduce_sum(ctx, ctx->scal.p, 1));
-        }
+        if (norm2) MFB_TRY(finish(1));
         return MFB_OK;
     }
     int axpby_batch_dev(int k, double* const* ys, const double* a, const double* const* ap, const double* b,
@@ -579,8 +582,7 @@ struct Solver {
         double* partials = norm2 ? ctx->scal.p + 64 : nullptr;
         LAUNCH(k_lincomb, RED_BLOCKS, TPB, L, n, partials, mask(), ctx->n_var);
         if (norm2) {
-            LAUNCH(k_reduce_partials, 1, 256, partials, RED_BLOCKS, ctx->scal.p);
-            MFB_TRY(mfb_allreduce_sum(ctx, ctx->scal.p, 1));
+            MFB_TRY(finish(1));
             MFB_CUDA(cudaMemcpyAsync(ctx->h_scal, ctx->scal.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
             MFB_CUDA(cudaStreamSynchronize(ctx->stream));
             *norm2 = ctx->h_scal[0];
@@ -1318,6 +1320,7 @@ extern "C" int mfb_krylov_solve_ex(mfb_ctx* ctx, int method, int s, int maxiter,
     MFB_CUDA(cudaStreamSynchronize(ctx->stream));
     Ks.release();
     plv.release();
+    MFB_TRY(mfb_p2p_check(ctx));
     if (info) *info = inf;
     return inf.converged ? MFB_OK : MFB_NOT_CONVERGED;
 }
