@@ -36,6 +36,8 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--assembly-only", action="store_true", help="development aid: skip the Krylov solve in every step "
                                                                 "(prints timings of the assembly only; never a bench value)")
+    p.add_argument("--workload", default="neo_hookean", choices=["neo_hookean", "linear_elasticity", "thermo_elasticity", "j2"],
+                   help="development aid with --assembly-only: time the assembly of another BASELINE config (box side from --box)")
     p.add_argument("--spmv-sweep", action="store_true", help="development aid: time the SpMV tuning variants on the assembled "
                                                              "matrix and exit")
     p.add_argument("--ncu", action="store_true", help="profiler capture run: exactly W warm-up steps, no e2e pass; "
@@ -207,8 +209,13 @@ def main():
     t_setup = time.perf_counter()
     n = args.n
     gtables = fmesh.box_tables((1.0, 1.0, 1.0), (n, n, n), "CUBE", groups=("left", "right"), numbering=args.numbering)
-    spec = wf.neo_hookean(fixed_bg=1, traction_bg=2)
-    ndof_global = 3 * gtables.variable_size
+    if args.workload != "neo_hookean" and not args.assembly_only:
+        raise SystemExit("--workload other than neo_hookean is an --assembly-only development aid; the bench line is configs[2]")
+    spec = {"neo_hookean": lambda: wf.neo_hookean(fixed_bg=1, traction_bg=2),
+            "linear_elasticity": lambda: wf.linear_elasticity(0.5769, 0.3846, 1000.0, fixed_bg=1, traction_bgs=((2, "sl"),)),
+            "thermo_elasticity": lambda: wf.thermo_elasticity(fixed_bg=1, thermal_bg=2),
+            "j2": lambda: wf.j2_plasticity(fixed_bg=1, traction_bg=2)}[args.workload]()
+    ndof_global = len(spec["basic_vars"]) * gtables.variable_size
     gstate = initial_state(gtables.x, 1.0 / n)
     if world > 1:
         from metafem_jl_b200.frontend import partition as pt
@@ -232,12 +239,22 @@ def main():
         with torch.cuda.stream(stream):
             m.init_distributed(fd, sub, rank, world, bytes(idt.cpu().numpy().tobytes()))
     for b, v in zip(("d1", "d2", "d3"), gstate):
-        fd.controlpoints[b][:] = v
-    fd.controlpoints["Pl1"][:] = LOAD
-    fd.global_vars.update(mu=MU, lam=LAM, tau_b=1000 * max(MU, LAM))
+        fd.controlpoints[b][:] = v * (1.0 if args.workload == "neo_hookean" else 0.05)
+    if args.workload == "neo_hookean":
+        fd.controlpoints["Pl1"][:] = LOAD
+        fd.global_vars.update(mu=MU, lam=LAM, tau_b=1000 * max(MU, LAM))
+    elif args.workload == "thermo_elasticity":
+        fd.controlpoints["T"][:] = 20.0 * np.cos(tables.x[1])
+        fd.controlpoints["Te"][:] = 300.0
+    elif args.workload == "j2":
+        fd.controlpoints["sl1"][:] = 120.0
+    else:
+        fd.controlpoints["sl1"][:] = 0.01
     fd.globalfield.converge_tol = TOL
     m.assemble_Global_Variables(fd)
     m.compile_Updater_GPU(1, fd)
+    if args.workload == "j2":
+        j2 = m.api.J2MaterialState(fd, Y_initial=100.0, lam=0.0, mu=50e3, Eb=12.5e3, Ep=25e3, f_res=1.0)
     gf, td = fd.globalfield, fd.time_discretization
     m.api.update_Time(gf, td)
     ndof, nnz = gf.basicfield_size, gf.nnz
@@ -245,9 +262,10 @@ def main():
     gam = np.array(td.gamma_params)
     fd.sync_fields()
     fd.ctx.call("mfb_assemble_linear", L.ptr(kp), len(kp))        # K_linear_func: once per time step, outside the Newton loop
-    x_host = torch.empty(ndof, dtype=torch.float64).pin_memory()
+    nx = (gf.max_time_level + 1) * ndof
+    x_host = torch.empty(nx, dtype=torch.float64).pin_memory()
     x_host.numpy()[:] = fd.get_vector(L.VEC_X)
-    dx_host = torch.empty(ndof, dtype=torch.float64).pin_memory()
+    dx_host = torch.empty(nx, dtype=torch.float64).pin_memory()
     t_setup = time.perf_counter() - t_setup
     import ctypes as C
     info = L.SolveInfo()
@@ -255,9 +273,14 @@ def main():
 
     def step(e2e):
         if e2e:
-            fd.ctx.call("mfb_vector_set", L.VEC_X, L.ptr(x_host), ndof)
+            fd.ctx.call("mfb_vector_set", L.VEC_X, L.ptr(x_host), nx)
         fd.ctx.call("mfb_initialize_dx", gf.dt, L.ptr(gam), len(gam))
         fd.ctx.call("mfb_update_x_star", L.ptr(alpha), len(alpha))
+        if args.assembly_only and args.workload != "neo_hookean":
+            fd.ctx.call("mfb_assemble_linear", L.ptr(kp), len(kp))      # K_linear_func is part of every time step there
+        if args.workload == "j2":
+            fd.ctx.call("mfb_eval_qp_args", gf.t, gf.dt)
+            j2()
         fd.ctx.call("mfb_assemble_nonlinear", L.ptr(kp), len(kp), gf.t, gf.dt)
         fd.ctx.call("mfb_residue_norm", C.byref(res))
         if args.assembly_only:
@@ -266,7 +289,7 @@ def main():
                     None, C.byref(info))
         fd.ctx.call("mfb_update_dx", L.ptr(beta), len(beta), -1.0)
         if e2e:
-            fd.ctx.call("mfb_vector_get", L.VEC_DX, L.ptr(dx_host), ndof)
+            fd.ctx.call("mfb_vector_get", L.VEC_DX, L.ptr(dx_host), nx)
 
     def timed(e2e, steps):
         if world > 1:
@@ -319,7 +342,9 @@ def main():
     if rank != 0:
         return
     if args.assembly_only:
-        print(json.dumps({"assembly_only": True, "assembly_ms": pms[1] / max(pcnt[1], 1), "element_kernel_ms": pms[4] / max(pcnt[4], 1),
+        print(json.dumps({"assembly_only": True, "workload": args.workload, "dof": ndof_global, "nnz": nnz, "step_ms": ms_total / K,
+                          "K_linear_ms": pms[2] / max(pcnt[2], 1),
+                          "assembly_ms": pms[1] / max(pcnt[1], 1), "element_kernel_ms": pms[4] / max(pcnt[4], 1),
                           "boundary_kernels_ms": pms[7] / max(pcnt[7], 1), "clocks": clk}))
         return
     ms_step = ms_total / K
@@ -362,7 +387,7 @@ def main():
                               "peak_kind": "measured live (mfb_measure_fp64_peak: register-resident DFMA chains)",
                               "flops_executed": flops_exec, "reference_equivalent_tflops": 2.62e6 * n_el / (elem_ms * 1e-3) / 1e12,
                               "hbm_algorithmic_bytes": asm_bytes, "hbm_frac": asm_bytes / (elem_ms * 1e-3) / 1e9 / peak},
-        "e2e": {"value": e2e_val, "unit": "DOF/s", "h2d_bytes_per_step": 8 * ndof, "d2h_bytes_per_step": 8 * ndof + 8,
+        "e2e": {"value": e2e_val, "unit": "DOF/s", "h2d_bytes_per_step": 8 * nx, "d2h_bytes_per_step": 8 * nx + 8,
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": int(launches), "clocks": clk,
     }
