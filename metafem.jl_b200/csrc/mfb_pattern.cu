@@ -86,11 +86,6 @@ __global__ void k_invert(const int* iperm, int64_t N, int* perm) {
     if (i < N) perm[iperm[i]] = (int)i;
 }
 
-__global__ void k_renumber(const int* conn_ref, const int* perm, int64_t n, int* conn) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) conn[i] = perm[conn_ref[i]];
-}
-
 __global__ void k_pair_keys(const int* conn, int n_a, int64_t n_el, unsigned long long* keys) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t total = n_el * n_a * n_a;

@@ -69,7 +69,8 @@ def _form(name, spec, blk, n_a, n_q, linear, evalk=False):
     nsd, ks = len(dslots), len(bslots)
     nd = nv * nsd * nv * ks
     tl = _tile(n_a, nv) if terms else dict(NTC=2, CG=1, W=1, LPW=1)
-    tpb = 32 * max(tl["W"] if terms else 2, 2)
+    import os
+    tpb = 32 * max((tl["W"] + int(os.environ.get("MFB_EXTRA_WARPS", "0"))) if terms else 2, 2)
     lines = []
     lines.append(f"struct {name} {{")
     lines.append(f"  static constexpr int NV = {nv}, NA = {n_a}, NQ = {n_q}, L1 = {L1}, BOUNDARY = {boundary}, "
