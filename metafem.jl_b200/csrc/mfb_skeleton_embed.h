@@ -91,6 +91,7 @@ __device__ __forceinline__ double inv3(const double (&J)[3][3], double (&I)[3][3
 //                        W (warps with tangent tiles), LPW (tiles = active lanes per warp), CG (column groups),
 //                        NTC (even; columns per tile, CG*NTC >= NA), SMEM (bytes);
 //   __device__ static constexpr int dslot(int i), bslot(int i);        // slot ids (0:N, 1..3: d/dx) of the used dual/base slots
+//   static constexpr int NGS; gslot(slot) -> storage index of a slot in G (or -1), gslot_id(k) -> slot id of storage index k
 //   __device__ static constexpr int wslot(int k), wlev(int k), wpos(int k);   // inner word k: slot, time level, variable
 //   __device__ static constexpr int cslot(int k), cfield(int k);              // cp word k: slot, field index
 //   static constexpr int EVAL (0/1), NQPI (integration-point words read), NQPO (callback arguments written);
@@ -127,15 +128,16 @@ struct Smem {
     static constexpr int NDS = F::ND > 0 ? F::NV * DPS : 1;
     static constexpr int NVLI = F::LINEAR ? 0 : F::L1 * F::NV;   // field components interpolated: unknowns at every level ...
     static constexpr int NVL = NVLI + F::NC;                     // ... then the CONTROLPOINT_VAR fields
+    static constexpr int NGS = F::NGS;                           // gradient slots actually stored (used by a dual, a base or a residual term)
+    static constexpr int RLD = (NVL > 0 ? NVL : 1) * 4;          // leading dimension of gu, and of R which reuses its storage
     struct alignas(16) GD {
-        double G[F::NQ][4][NAP];
+        double G[F::NQ][NGS > 0 ? NGS : 1][NAP];   // G[q][gslot(slot)][a]
         double D[F::NQ][NDS];                      // D[q][dp][(dsi*NV + bp)*KS + ks], dp stride DPS
     };
     struct alignas(16) Geo {
         double I[F::NQ][9];                        // Jacobian, then its inverse
         double wgt[F::NQ];
         double nrm[F::NQ][3];
-        double gu[F::NQ][NVL > 0 ? NVL : 1][4];    // value and reference gradient of every field component
     };
     union {
         GD gd;
@@ -145,7 +147,9 @@ struct Smem {
         Geo geo;                                   // phases B1..B3
         int em[F::HAS_K ? F::NA * F::NA : 1];      // phases C, D: node pair -> block-CSR entry of this element
     };
-    double R[F::NQ][F::NV * 4];
+    // gu[q][var][X]: value (X = 0) and reference gradient of every field component (phases B1..B3). The point-function
+    // thread of q-point q overwrites ITS row with the weighted residual integrands R[q][v*4 + slot] once it has read it.
+    alignas(16) double gu[F::NQ][RLD];
     double xe[F::NA][3];
     double ue[F::L1][F::NA][F::NV];
     double ce[F::NC > 0 ? F::NC : 1][F::NA];
@@ -161,6 +165,8 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
     constexpr int NA = F::NA, NQ = F::NQ, NV = F::NV, BB = NV * NV, MROWS = NA * NV * NV, TPB = F::TPB;
     constexpr int NVLI = Smem<F>::NVLI, NVL = Smem<F>::NVL;
     static_assert(TPB >= 64 && TPB % 32 == 0, "the block needs one point-function warp and at least one geometry warp");
+    static_assert(!F::HAS_RES || NVL >= NV, "R reuses the storage of gu");
+    constexpr int NGS = F::NGS;
 
     for (long long item = blockIdx.x; item < A.n_items; item += gridDim.x) {
         long long e = item;
@@ -223,7 +229,7 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
                 S.geo.I[q][2 * 3 + X - 1] = j2;
             }
 #pragma unroll
-            for (int v = 0; v < NVL; ++v) S.geo.gu[q][v][X] = acc[v];
+            for (int v = 0; v < NVL; ++v) S.gu[q][v * 4 + X] = acc[v];
         }
         __syncthreads();
         // ---- phase B2: inverse, weight, normal -----------------------------------------------
@@ -269,7 +275,7 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
                 for (int k = 0; k < F::NW + F::NCW; ++k) {
                     const int slot = k < F::NW ? F::wslot(k) : F::cslot(k - F::NW);
                     const int var = k < F::NW ? F::wlev(k) * NV + F::wpos(k) : NVLI + F::cfield(k - F::NW);
-                    const double* gu = S.geo.gu[q][var];
+                    const double* gu = &S.gu[q][var * 4];
                     const double v = slot == 0 ? gu[0]
                                                : (gu[1] * I[0 * 3 + slot - 1] + gu[2] * I[1 * 3 + slot - 1]) + gu[3] * I[2 * 3 + slot - 1];
                     if (k < F::NW) w[k] = v; else c[k - F::NW] = v;
@@ -297,7 +303,8 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
                     for (int k = 0; k < F::ND; ++k) D[k] = 0.0;
                     F::point(w, c, nrm, qv, A, R, D);
 #pragma unroll
-                    for (int k = 0; k < NV * 4; ++k) S.R[q][k] = R[k] * wgt;
+                    if constexpr (F::HAS_RES)
+                        for (int k = 0; k < NV * 4; ++k) S.gu[q][k] = R[k] * wgt;       // all words of this q are in registers by now
                     if constexpr (F::ND > 0) {
                         constexpr int DPB = Smem<F>::DPB, DPS = Smem<F>::DPS;
 #pragma unroll
@@ -310,9 +317,12 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
                 const int q = o / NA, a = o - q * NA;
                 const double d0 = ref[(1 * NQ + q) * NA + a], d1 = ref[(2 * NQ + q) * NA + a], d2 = ref[(3 * NQ + q) * NA + a];
                 const double* I = S.geo.I[q];
-                S.gd.G[q][0][a] = ref[(0 * NQ + q) * NA + a];
 #pragma unroll
-                for (int s = 0; s < 3; ++s) S.gd.G[q][1 + s][a] = (d0 * I[0 * 3 + s] + d1 * I[1 * 3 + s]) + d2 * I[2 * 3 + s];
+                for (int k = 0; k < NGS; ++k) {
+                    const int s = F::gslot_id(k);                    // slot id of storage index k: 0 = N, 1..3 = d/dx
+                    S.gd.G[q][k][a] = s == 0 ? ref[(0 * NQ + q) * NA + a]
+                                             : (d0 * I[0 * 3 + s - 1] + d1 * I[1 * 3 + s - 1]) + d2 * I[2 * 3 + s - 1];
+                }
             }
         }
         if constexpr (F::EVAL) continue;
@@ -341,13 +351,15 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
 #pragma unroll 1
                 for (int q = 0; q < NQ; ++q) {
                     // stage 1 (registers): T[bp][ks] = sum_d G[q][dslot(d)][a] * D[q][dp][d][bp][ks]
-                    double g4[4];
+                    double gs[NGS > 0 ? NGS : 1];
 #pragma unroll
-                    for (int sl = 0; sl < 4; ++sl) g4[sl] = S.gd.G[q][sl][a];
+                    for (int k = 0; k < NGS; ++k) gs[k] = S.gd.G[q][k][a];
                     if (F::HAS_RES && cgi == 0) {
-                        const double2 r01 = *reinterpret_cast<const double2*>(&S.R[q][dp * 4]);
-                        const double2 r23 = *reinterpret_cast<const double2*>(&S.R[q][dp * 4 + 2]);
-                        racc += (g4[0] * r01.x + g4[1] * r01.y) + (g4[2] * r23.x + g4[3] * r23.y);
+                        const double2 r01 = *reinterpret_cast<const double2*>(&S.gu[q][dp * 4]);
+                        const double2 r23 = *reinterpret_cast<const double2*>(&S.gu[q][dp * 4 + 2]);
+                        const double r4[4] = {r01.x, r01.y, r23.x, r23.y};
+#pragma unroll
+                        for (int k = 0; k < NGS; ++k) racc += gs[k] * r4[F::gslot_id(k)];
                     }
                     double dv[DPS];
                     const double2* Dq = reinterpret_cast<const double2*>(&S.gd.D[q][dp * DPS]);
@@ -363,13 +375,13 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
                         for (int ks = 0; ks < KS; ++ks) {
                             double tv = 0.0;
 #pragma unroll
-                            for (int d = 0; d < NSD; ++d) tv += g4[F::dslot(d)] * dv[(d * NV + bp) * KS + ks];
+                            for (int d = 0; d < NSD; ++d) tv += gs[F::gslot(F::dslot(d))] * dv[(d * NV + bp) * KS + ks];
                             T[bp][ks] = tv;
                         }
                     // stage 2: rank-KS update of the lane's NV x NTC tile
 #pragma unroll
                     for (int ks = 0; ks < KS; ++ks) {
-                        const double2* gp = reinterpret_cast<const double2*>(&S.gd.G[q][F::bslot(ks)][b0]);
+                        const double2* gp = reinterpret_cast<const double2*>(&S.gd.G[q][F::gslot(F::bslot(ks))][b0]);
 #pragma unroll
                         for (int c = 0; c < NTC / 2; ++c) {
                             const double2 v = gp[c];
@@ -416,7 +428,7 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
                 double s = 0.0;
                 for (int q = part * QCH; q < q1; ++q) {
 #pragma unroll
-                    for (int sl = 0; sl < 4; ++sl) s += S.gd.G[q][sl][a] * S.R[q][v * 4 + sl];
+                    for (int k = 0; k < NGS; ++k) s += S.gd.G[q][k][a] * S.gu[q][v * 4 + F::gslot_id(k)];
                 }
                 if (s != 0.0) red_add(A.res + (size_t)S.node[a] * NV + v, s);
             }

@@ -68,6 +68,7 @@ def _form(name, spec, blk, n_a, n_q, linear, evalk=False):
     bslots = sorted({_slot(t["deriv_sd"]) for t in terms})
     nsd, ks = len(dslots), len(bslots)
     nd = nv * nsd * nv * ks
+    gslots = sorted(set(dslots) | set(bslots) | {_slot(t["dual_sd"]) for t in residues})      # gradient slots G must hold
     tl = _tile(n_a, nv) if terms else dict(NTC=2, CG=1, W=1, LPW=1)
     import os
     tpb = 32 * max((tl["W"] + int(os.environ.get("MFB_EXTRA_WARPS", "0"))) if terms else 2, 2)
@@ -78,7 +79,9 @@ def _form(name, spec, blk, n_a, n_q, linear, evalk=False):
                  f"HAS_RES = {int(bool(residues))}, HAS_K = {int(bool(terms))}, TPB = {tpb}, "
                  f"NSD = {nsd}, KS = {ks}, ND = {nd}, NTC = {tl['NTC']}, CG = {tl['CG']}, W = {tl['W']}, "
                  f"LPW = {tl['LPW']}, SMEM = @SMEM@, "
-                 f"EVAL = {int(evalk)}, NQPI = {len(qpw)}, NQPO = {len(qpo)};")
+                 f"EVAL = {int(evalk)}, NQPI = {len(qpw)}, NQPO = {len(qpo)}, NGS = {len(gslots)};")
+    lines.append(_table("gslot", [gslots.index(sl) if sl in gslots else -1 for sl in range(4)]))
+    lines.append(_table("gslot_id", gslots))
     lines.append(_table("dslot", dslots))
     lines.append(_table("bslot", bslots))
     lines.append(_table("wslot", [_slot(w["sd"]) for w in inner]))
@@ -132,12 +135,12 @@ def _form(name, spec, blk, n_a, n_q, linear, evalk=False):
     nap = n_a + (n_a & 1)
     dpb = nsd * nv * ks
     nds = nv * (dpb + (dpb & 1)) if nd else 1
-    gd = _align16(8 * (n_q * 4 * nap + n_q * nds))
+    gd = _align16(8 * (n_q * max(len(gslots), 1) * nap + n_q * nds))
     ke = 8 * (mrows * n_a if terms else 1)
     nvl = (0 if linear else L1 * nv) + len(fields)
-    geo = _align16(max(8 * n_q * (9 + 1 + 3 + 4 * max(nvl, 1)), 4 * n_a * n_a if terms else 4))
-    smem = _align16(max(gd, ke)) + geo + 8 * (n_q * nv * 4 + n_a * 3 + L1 * n_a * nv
-                                             + max(len(fields), 1) * n_a) + 4 * n_a + 32
+    geo = _align16(max(8 * n_q * (9 + 1 + 3), 4 * n_a * n_a if terms else 4))
+    smem = _align16(_align16(max(gd, ke)) + geo + 8 * (n_q * 4 * max(nvl, 1) + n_a * 3 + L1 * n_a * nv
+                                                      + max(len(fields), 1) * n_a) + 4 * n_a)
     body = "\n".join(lines).replace("@SMEM@", str(smem))
     return body, fields, globs, smem, bool(terms), tpb, [w["sym"] for w in qpw], [n for _, n in qpo]
 
@@ -150,7 +153,7 @@ def _is_number(s):
         return False
 
 
-def _min_blocks(tpb, smem, regs=184):
+def _min_blocks(tpb, smem, regs=170):
     """Resident blocks per SM to ask of __launch_bounds__: what 227 KB of shared memory allow (1 KB reserved per block),
     capped so that every thread keeps at least ``regs`` registers of the 64 K file."""
     import os
