@@ -314,10 +314,12 @@ def main():
                                                 fd.ctx.call("mfb_assemble_nonlinear", L.ptr(kp), len(kp), gf.t, gf.dt))
         out = {}
         for rnd in range(2):
-            for v in range(10):
-                ms = C.c_double(0.0)
-                fd.ctx.call("mfb_spmv_variant_bench", v, 20, C.byref(ms))
+            for v in (0, 8, 10, 11, 12, 13):
+                ms, diff = C.c_double(0.0), C.c_double(0.0)
+                fd.ctx.call("mfb_spmv_variant_bench", v, 20, C.byref(ms), C.byref(diff) if rnd == 0 else None)
                 out.setdefault(v, []).append(round(ms.value, 4))
+                if rnd == 0:
+                    out[v].append(f"maxdiff={diff.value:.2e}")
         print(json.dumps({"spmv_sweep_ms": out}))
         return
     if not args.ncu:

@@ -206,7 +206,7 @@ int mfb_j2_update_states(mfb_ctx *ctx, const char *prefix);
 int mfb_spmv(mfb_ctx *ctx, int which_matrix, const double *x, double *y, int64_t n);
 
 /* Development aid: ms per launch of one tuning variant of the 3-variable block SpMV on K_total (0 = production kernel). */
-int mfb_spmv_variant_bench(mfb_ctx *ctx, int variant, int reps, double *ms_per_launch);
+int mfb_spmv_variant_bench(mfb_ctx *ctx, int variant, int reps, double *ms_per_launch, double *max_abs_diff);
 
 typedef struct {
     int32_t passes;        /* restart passes used */

@@ -104,6 +104,92 @@ __global__ void __launch_bounds__(256, MINB) k_spmv_bsr(const int* __restrict__ 
     }
 }
 
+// Same kernel with the software pipeline running ACROSS row boundaries: while the last batch of a row is consumed, the
+// first batch of the warp's next row is already in flight (its row pointers were fetched one row earlier), so the
+// dependent chain nodeptr -> (values, column ids) -> x[col] is never restarted from an empty pipeline.
+template <int NV, int UNR, int ROWS = SPMV_ROWS>
+__global__ void __launch_bounds__(256) k_spmv_bsr_x(const int* __restrict__ nodeptr, const int* __restrict__ nodecol,
+                                                    const double* __restrict__ K, const double* __restrict__ x,
+                                                    double* __restrict__ y, int64_t N) {
+    constexpr int B = NV * NV, EPW = 32 / B, ACTIVE = EPW * B;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int le = lane / B, ik = lane - le * B, i = ik / NV, k = ik - i * NV;
+    const bool on = lane < ACTIVE;
+    const double* xk = x + k;
+    int64_t row = blockIdx.x * (int64_t)ROWS + warp;
+    const int64_t rend = min((blockIdx.x + 1) * (int64_t)ROWS, N);
+    if (row >= rend) return;
+    int s = nodeptr[row], t = nodeptr[row + 1];
+    int64_t nrow = row + 8;
+    int ns = 0, nt = 0;
+    if (nrow < rend) { ns = __ldg(nodeptr + nrow); nt = __ldg(nodeptr + nrow + 1); }
+    int base = 0;                                            // first entry of the current batch within its row (warp-uniform)
+    const double* Kp = K + (size_t)s * B + lane;
+    const int* Cp = nodecol + s + le;
+    double v[UNR], a[UNR];
+    int c[UNR];
+    {
+        const int deg = on ? t - s : 0;
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            a[u] = 0.0;
+            const bool ok = le + u * EPW < deg;
+            v[u] = ok ? __ldcs(Kp + u * ACTIVE) : 0.0;
+            c[u] = ok ? __ldg(Cp + u * EPW) : 0;
+        }
+    }
+    while (true) {
+        const bool last = base + UNR * EPW >= t - s;         // this batch finishes the row
+        int64_t row_n = row;
+        int s_n = s, t_n = t, base_n = base + UNR * EPW;
+        if (last) {
+            row_n = nrow; s_n = ns; t_n = nt; base_n = 0;
+            nrow += 8;
+            if (nrow < rend) { ns = __ldg(nodeptr + nrow); nt = __ldg(nodeptr + nrow + 1); }
+            Kp = K + (size_t)s_n * B + lane;
+            Cp = nodecol + s_n + le;
+        } else {
+            Kp += UNR * ACTIVE;
+            Cp += UNR * EPW;
+        }
+        const bool more = row_n < rend;
+        double vn[UNR];
+        int cn[UNR];
+        {
+            const int deg = (on && more) ? t_n - s_n : 0;
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const bool ok = base_n + le + u * EPW < deg;
+                vn[u] = ok ? __ldcs(Kp + u * ACTIVE) : 0.0;
+                cn[u] = ok ? __ldg(Cp + u * EPW) : 0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) a[u] += v[u] * __ldg(xk + (size_t)c[u] * NV);
+        if (last) {
+            double acc = 0.0;
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) { acc += a[u]; a[u] = 0.0; }
+            double tt = acc;
+#pragma unroll
+            for (int d = 1; d < NV; ++d) tt += __shfl_down_sync(0xffffffffu, acc, d);          // sum over k
+            double r = tt;
+            if constexpr ((B & (B - 1)) == 0) {
+#pragma unroll
+                for (int o = 16; o >= B; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+            } else {
+#pragma unroll
+                for (int d = 1; d < EPW; ++d) r += __shfl_down_sync(0xffffffffu, tt, d * B);   // sum over the EPW entries
+            }
+            if (le == 0 && k == 0 && on) y[(size_t)row * NV + i] = r;
+        }
+        if (!more) break;
+        row = row_n; s = s_n; t = t_n; base = base_n;
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) { v[u] = vn[u]; c[u] = cn[u]; }
+    }
+}
+
 // SpMV (fallback, any NV): the row's values as one flat stream, (entry, i, k) recomputed per value.
 template <int NV>
 __global__ void __launch_bounds__(256) k_spmv_bsr_flat(const int* __restrict__ nodeptr, const int* __restrict__ nodecol,
@@ -1332,7 +1418,7 @@ extern "C" int mfb_krylov_solve(mfb_ctx* ctx, int method, int s, int maxiter, in
 
 // Development aid (bench.py --spmv-sweep): times `reps` launches of one (unroll, min-blocks, rows-per-CTA) variant of the
 // NV = 3 block SpMV on K_total with CUDA events; variant 0 is the production kernel. Returns ms per launch.
-extern "C" int mfb_spmv_variant_bench(mfb_ctx* ctx, int variant, int reps, double* ms_out) {
+extern "C" int mfb_spmv_variant_bench(mfb_ctx* ctx, int variant, int reps, double* ms_out, double* max_abs_diff) {
     if (!ctx || !ms_out) return MFB_ERR_ARG;
     MFB_REQUIRE(ctx->U > 0 && ctx->n_var == 3, MFB_ERR_STATE, "mfb_spmv_variant_bench: needs a built 3-variable system");
     MFB_CUDA(cudaSetDevice(ctx->device));
@@ -1357,10 +1443,14 @@ extern "C" int mfb_spmv_variant_bench(mfb_ctx* ctx, int variant, int reps, doubl
             case 7: LAUNCH((k_spmv_bsr<3, 5, 5, 32>), g(32), 256, np, nc, K, x, y, N); break;
             case 8: LAUNCH((k_spmv_bsr<3, 4, 6, 128>), g(128), 256, np, nc, K, x, y, N); break;
             case 9: LAUNCH((k_spmv_bsr<3, 2, 8, 64>), g(64), 256, np, nc, K, x, y, N); break;
+            case 10: LAUNCH((k_spmv_bsr_x<3, 5, 64>), g(64), 256, np, nc, K, x, y, N); break;
+            case 11: LAUNCH((k_spmv_bsr_x<3, 4, 64>), g(64), 256, np, nc, K, x, y, N); break;
+            case 12: LAUNCH((k_spmv_bsr_x<3, 3, 64>), g(64), 256, np, nc, K, x, y, N); break;
+            case 13: LAUNCH((k_spmv_bsr_x<3, 5, 128>), g(128), 256, np, nc, K, x, y, N); break;
             default: break;
         }
     };
-    MFB_REQUIRE(variant >= 0 && variant <= 9, MFB_ERR_ARG, "unknown SpMV variant");
+    MFB_REQUIRE(variant >= 0 && variant <= 13, MFB_ERR_ARG, "unknown SpMV variant");
     for (int i = 0; i < 3; ++i) launch(variant);
     MFB_CUDA(cudaEventRecord(e0, ctx->stream));
     for (int i = 0; i < reps; ++i) launch(variant);
@@ -1371,6 +1461,16 @@ extern "C" int mfb_spmv_variant_bench(mfb_ctx* ctx, int variant, int reps, doubl
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *ms_out = ms / reps;
+    if (max_abs_diff) {                                   // compare with the production kernel on the same x
+        std::vector<double> yv(n), y0(n);
+        MFB_CUDA(cudaMemcpyAsync(yv.data(), y, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        launch(0);
+        MFB_CUDA(cudaMemcpyAsync(y0.data(), y, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+        double d = 0.0;
+        for (int64_t q = 0; q < n; ++q) d = std::max(d, std::fabs(yv[q] - y0[q]));
+        *max_abs_diff = d;
+    }
     return MFB_OK;
 }
 
