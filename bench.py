@@ -93,6 +93,23 @@ class ClockSampler:
         return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=int(rows[0][1]), reasons=reasons, samples=len(rows))
 
 
+def ncu_traffic(prefix):
+    """DRAM bytes per launch (read + write) of the kernel from the newest committed ncu --set full summary under profiles/
+    (profiles/summarize.py writes them from the .ncu-rep brought back by gpurun); None if there is none."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"{prefix}_*_summary.txt")))   # round tags sort by name
+    if not files:
+        return None, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for line in open(files[-1]):
+        m = re.match(r"dram__bytes_(read|write)\.sum\s+(\w+)\s+([0-9.]+)", line)
+        if m:
+            tot += float(m.group(3)) * unit.get(m.group(2), 1.0)
+    return (tot or None), os.path.relpath(files[-1], ROOT)
+
+
 def hbm_peak():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
@@ -363,6 +380,8 @@ def main():
     fp64_peak = C.c_double(0.0)
     fd.ctx.call("mfb_measure_fp64_peak", C.byref(fp64_peak))
     asm_bytes = 8.0 * nnz + 8.0 * ndof + 8.0 * ndof + 24.0 * tables.variable_size + 4.0 * 20 * n_el + 4.0 * 400 * n_el
+    spmv_traffic, spmv_src = ncu_traffic("prof_spmv")
+    elem_traffic, elem_src = ncu_traffic("prof_elem")
     out = {
         "metric": "newton_step_dof_per_s", "value": value, "unit": "DOF/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -378,7 +397,8 @@ def main():
         "spmv_share_of_step": pms[0] / ms_total,
         "halo_exchange_ms_per_step": pms[5] / K, "krylov_reductions_ms_per_step": pms[6] / K,
         "roofline": {"bound": "hbm", "kernel": "k_spmv_bsr<3>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                     "frac": achieved / peak, "traffic": spmv_traffic if world == 1 else None, "traffic_source": spmv_src,
+                     "peak_kind": peak_kind,
                      "algorithmic_bytes": spmv_bytes, "launches_timed": int(pcnt[0]), "avg_ms": spmv_ms},
         # element kernel: FP64-pipe bound for hex20 x 27. "achieved" counts the flops the sum-factorised kernel
         # EXECUTES in its tangent/residual contraction (2*NQ*NA*NV*(NSD*NV*KS + NV*NA*KS + 4) = 0.68 Mflop/element); the
@@ -388,7 +408,8 @@ def main():
                               "frac": flops_exec / (elem_ms * 1e-3) / 1e12 / max(fp64_peak.value, 1e-9),
                               "peak_kind": "measured live (mfb_measure_fp64_peak: register-resident DFMA chains)",
                               "flops_executed": flops_exec, "reference_equivalent_tflops": 2.62e6 * n_el / (elem_ms * 1e-3) / 1e12,
-                              "hbm_algorithmic_bytes": asm_bytes, "hbm_frac": asm_bytes / (elem_ms * 1e-3) / 1e9 / peak},
+                              "hbm_algorithmic_bytes": asm_bytes, "hbm_frac": asm_bytes / (elem_ms * 1e-3) / 1e9 / peak,
+                              "traffic": elem_traffic if world == 1 else None, "traffic_source": elem_src},
         "e2e": {"value": e2e_val, "unit": "DOF/s", "h2d_bytes_per_step": 8 * nx, "d2h_bytes_per_step": 8 * nx + 8,
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": int(launches), "clocks": clk,
