@@ -10,6 +10,9 @@ reference ships no tests, so the oracle cannot be checked against the reference 
 It IS pinned at solver tolerance against the committed result files of the reference's own
 examples (tests/test_oracle_golden.py): examples/thermal_conduction/3D_MetaFEM_Result.vtk and
 examples/linear_elasticity/stress_concentration/3D_MetaFEM.vtk (digests of both are committed
-as fixtures under tests/golden/ by tests/golden/make_golden.py). Element-level values are
+as fixtures under tests/golden/ by tests/golden/make_golden.py), and against the reference's
+known answers: the analytical load-displacement table of examples/hypo_elastic_plasticity/
+J2Plasticity.jl:223-228 (tests/test_oracle_j2.py: callback semantics, history variables, second time
+derivatives) and the closed form of static_Neo_Hookean.jl:124. Element-level values are
 "parity unpinned" beyond that.
 """
