@@ -130,3 +130,38 @@ def test_j2_load_steps(pair):
     assert ost.Y.max() > J2_PARAMS["Y_initial"] + 1.0, "the load path must have hardened some points"
     assert np.abs(pst.state("Y") - ost.Y).max() < 1e-2 * (ost.Y.max() - J2_PARAMS["Y_initial"])
     assert np.abs(pst.state("ep1") - ost.ep[0]).max() < 1e-2 * np.abs(ost.ep[0]).max()
+
+
+def test_j2_cuda_path_matches_analytical_table(built_lib):
+    """The script's loading loop (J2Plasticity.jl:264-283) entirely on the CUDA path -- update_OneStep!, built-in return
+    map, update_States!, dessemble_X! -- against the script's analytical load-displacement table (:223-228, group 1:
+    isotropic hardening, loading into yield and partial unloading)."""
+    import metafem_b200 as m
+    EY = 100e3
+    s_tests, d1_ana = [40, 80, 100, 120, 140, 180, 200, 180, 100], [4, 8, 10, 16, 22, 34, 40, 38, 30]
+    dom, spec, mesh = build_case("j2", (5, 2, 2), size=(10.0, 1.0, 1.0))
+    for k in dom.cp:
+        dom.cp[k][:] = 0.0
+    fd = product_from_oracle(dom)
+    try:
+        fd.globalfield.converge_tol, fd.globalfield.dt = 1e-3, 1.0
+        m.assemble_Global_Variables(fd)
+        m.compile_Updater_GPU(1, fd)
+        st = m.api.J2MaterialState(fd, Y_initial=100.0, lam=0.0, mu=EY / 2, Eb=0.0, Ep=EY / 2, f_res=1.0)
+        fd.callbacks["strain_updater"] = st
+        fd.linear_solver = lambda d: m.iterative_Solve(d, Sv_func="bicgstabl_GS!", maxiter=2000, max_pass=20, s=8)
+        right = np.abs(mesh.x[0] - 10.0) < 1e-6
+        for s, ana in zip(s_tests, d1_ana):
+            fd.controlpoints["sl1"][:] = s
+            for counter in range(300):
+                m.update_OneStep(fd.time_discretization, max_iter=3, fem_domain=fd)
+                m.dessemble_X(fd)
+                st.update_States()
+                if np.abs(fd.controlpoints["d1_t1"]).max() < 1e-4:
+                    break
+            else:
+                pytest.fail(f"load {s}: the viscous relaxation loop did not settle")
+            d1 = fd.controlpoints["d1"][right].mean()
+            assert abs(d1 - ana * 1e-3) < 0.03 * abs(ana * 1e-3) + 4e-4, (s, d1, ana * 1e-3)
+    finally:
+        fd.close()
