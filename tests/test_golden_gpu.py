@@ -101,3 +101,52 @@ def test_stress_concentration_3d_cuda_matches_reference_result(built_lib):
     for k in ("d1", "d2", "d3"):
         a, b = d[k][idx], g[k]
         assert np.linalg.norm(a - b) / np.linalg.norm(b) < 1e-4, k
+
+
+def test_cantilever_cuda_matches_beam_theory(built_lib):
+    """examples/linear_elasticity/cantilever/3D_Script.jl: 10 x 1 x 1 beam, hex20 (10, 4, 4), penalty-fixed left face, idrs!
+    s = 8 -- the script's two load cases against the Euler-Bernoulli deflection lines it plots (:118, :134)."""
+    import metafem_b200 as m
+    from metafem_jl_b200.frontend import weakform as wf
+    from helpers import box_faces
+    L_box, LW, en = 1.0, 10, 4
+    size, n = (L_box * LW, L_box, L_box), (en * LW // 4, en, en)
+    c, conn = rg.make_Brick(size, n, "CUBE")
+    tm = rg.construct_TotalMesh_3D(c, conn)
+    f = box_faces(tm, size)
+    groups = [f["left"], np.concatenate([f["front"], f["bottom"], f["top"]]), f["back"], f["right"]]
+    mesh = fm.mesh_Classical(tm, groups, "CUBE")
+    fm.update_Mesh(mesh)
+    E, nu = 1.0, 0.001
+    lam, mu = E * nu / ((1 + nu) * (1 - 2 * nu)), E / (2 * (1 + nu))
+    spec = wf.linear_elasticity(lam, mu, 1000 * E / L_box ** 2, fixed_bg=1, traction_bgs=((4, "sl"), (3, "s2")))
+    dom = oasm.Domain(mesh, spec)
+    dom.globalfield.converge_tol = 1e-5
+    fd = product_from_oracle(dom)
+    try:
+        m.assemble_Global_Variables(fd)
+        m.compile_Updater_GPU(1, fd)
+        fd.linear_solver = lambda d: m.iterative_Solve(d, Sv_func="idrs!", maxiter=2000, max_pass=20, s=8)
+        dx = L_box / en
+        mid = (np.abs(mesh.x[1] - L_box / 2) < 0.25 * dx) & (np.abs(mesh.x[2] - L_box / 2) < 0.25 * dx)
+        xs = mesh.x[0][mid]
+        h, l = L_box, L_box * LW
+        I = h ** 3 / 12
+        sig = 1e6
+        cases = [(("sl6", sig), ("s22", 0.0), sig * L_box / (6 * E * I) * (3 * l - xs) * xs ** 2),
+                 (("sl6", 0.0), ("s22", sig), sig / (24 * E * I) * (xs ** 2 + 6 * l ** 2 - 4 * l * xs) * xs ** 2)]
+        for (k1, v1), (k2, v2), ana in cases:
+            for k in ("d1", "d2", "d3"):
+                fd.controlpoints[k][:] = 0.0
+            m.assemble_X(fd)
+            fd.controlpoints[k1][:] = v1
+            fd.controlpoints[k2][:] = v2
+            hist = m.update_OneStep(fd.time_discretization, fem_domain=fd)
+            assert hist[-1] < 1e-5, hist
+            m.dessemble_X(fd)
+            num = fd.controlpoints["d2"][mid]
+            far = xs > 0.3 * l
+            # beam theory neglects shear deformation and the penalty compliance: a few percent at l/h = 10
+            assert np.abs(num[far] / ana[far] - 1.0).max() < 0.04, (num[far] / ana[far])
+    finally:
+        fd.close()
