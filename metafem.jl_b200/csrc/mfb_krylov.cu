@@ -341,11 +341,13 @@ struct LinComb {
     double c[MAXT];
     const double* x[MAXT];
     const double* cp[MAXT];   // optional device-resident factor: term i is c[i] * (*cp[i]) * x_i  (nullptr -> c[i] * x_i)
+    const double* ayp;        // optional device-resident factor of ay
 };
 
 // optional fused squared norm of the result (partials[block]); 4 independent elements per thread for memory-level parallelism
 __global__ void __launch_bounds__(TPB) k_lincomb(LinComb L, int64_t n, double* partial_norm2, const unsigned char* owned, int nv) {
     double nrm = 0.0;
+    if (L.ayp) L.ay *= __ldg(L.ayp);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
         double sv[4];
@@ -525,6 +527,46 @@ __global__ void k_sc_gamma(double* sc, int S) {                                 
 }
 __global__ void k_sc_store(double* sc, int at, const double* red) { sc[at] = red[0]; }
 
+// ---- device-resident scalars of idrs! (04_IDRs.jl:26-95). Layout: [0] omega [1] beta [2] alpha [8 + i] f [8 + S + i] c
+// [8 + 2S + i] -omega*c [8 + 3S + i*S + k] M[i][k]
+enum { ID_OMEGA = 0, ID_BETA = 1, ID_ALPHA = 2, ID_F = 8 };
+__global__ void k_idr_init(double* sc, int S) {
+    for (int i = threadIdx.x; i < 8 + 3 * S + S * S; i += blockDim.x) sc[i] = 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sc[ID_OMEGA] = 1.0;
+        for (int i = 0; i < S; ++i) sc[8 + 3 * S + i * S + i] = 1.0;           // M = I (:41)
+    }
+}
+__global__ void k_idr_f(double* sc, const double* red, int S) {                  // f = P' r (:47-49)
+    for (int i = threadIdx.x; i < S; i += blockDim.x) sc[ID_F + i] = red[i];
+}
+__global__ void k_idr_c(double* sc, int k, int S) {                              // c = LowerTriangular(M[k:s,k:s]) \ f[k:s] (:52)
+    double* f = sc + ID_F; double* c = sc + ID_F + S; double* oc = sc + ID_F + 2 * S; const double* M = sc + ID_F + 3 * S;
+    for (int i = k; i < S; ++i) {
+        double v = f[i];
+        for (int j = k; j < i; ++j) v -= M[i * S + j] * c[j];
+        c[i] = v / M[i * S + i];
+        oc[i] = -sc[ID_OMEGA] * c[i];
+    }
+}
+__global__ void k_idr_alpha(double* sc, const double* red, int i, int S) { sc[ID_ALPHA] = red[0] / sc[ID_F + 3 * S + i * S + i]; }   // (:66)
+__global__ void k_idr_M(double* sc, const double* red, int k, int S) {           // M[i][k] = P[i]' G[k], i >= k (:71-73); beta; f update
+    double* f = sc + ID_F; double* M = sc + ID_F + 3 * S;
+    for (int i = k; i < S; ++i) M[i * S + k] = red[i - k];
+    const double beta = f[k] / M[k * S + k];
+    sc[ID_BETA] = beta;
+    for (int i = k + 1; i < S; ++i) f[i] -= beta * M[i * S + k];                  // (:85)
+}
+__global__ void k_idr_omega(double* sc, const double* red) {                     // modify_Omega (:1-8)
+    const double n1 = sqrt(red[0]), n2 = sqrt(red[1]), d = red[2];
+    const double angle = 0.70710678118654752440;
+    const double rho = fabs(d / (n1 * n2));
+    double omega = d / (n1 * n1);
+    if (rho < angle) omega = omega * angle / rho;
+    sc[ID_OMEGA] = omega;
+}
+
 __global__ void k_div(double* y, const double* x, const double* d, int64_t n) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) y[i] = x[i] / d[i];
@@ -636,9 +678,9 @@ struct Solver {
     }
     // y = ay*y + sum (c_i * *cp_i) x_i with device-resident factors; optional fused ||y||^2 left in ctx->scal[0]
     int lincomb_dev(double* y, double ay, int k, const double* c, const double* const* cp, const double* const* xs,
-                    bool norm2 = false) {
+                    bool norm2 = false, const double* ayp = nullptr) {
         LinComb L;
-        L.y = y; L.ay = ay; L.n = k;
+        L.y = y; L.ay = ay; L.n = k; L.ayp = ayp;
         for (int i = 0; i < k; ++i) { L.c[i] = c[i]; L.cp[i] = cp[i]; L.x[i] = xs[i]; }
         double* partials = norm2 ? ctx->scal.p + 64 : nullptr;
         LAUNCH(k_lincomb, RED_BLOCKS, TPB, L, n, partials, mask(), ctx->n_var);
@@ -665,6 +707,7 @@ struct Solver {
         LinComb L;
         L.y = y; L.ay = ay; L.n = k;
         for (int i = 0; i < k; ++i) { L.c[i] = c[i]; L.x[i] = xs[i]; L.cp[i] = nullptr; }
+        L.ayp = nullptr;
         double* partials = norm2 ? ctx->scal.p + 64 : nullptr;
         LAUNCH(k_lincomb, RED_BLOCKS, TPB, L, n, partials, mask(), ctx->n_var);
         if (norm2) {
@@ -712,7 +755,9 @@ int true_residual(Solver& S, double* r, const double* b, const double* x, double
     return MFB_OK;
 }
 
-// idrs!  (04_IDRs.jl:26-95). Vectors: P[s], U[s], G[s], Ar.
+// idrs!  (04_IDRs.jl:26-95). Vectors: P[s], U[s], G[s], Ar. Same operations in the same order as the reference; M, f, c,
+// omega, alpha, beta live on the device (one-thread kernels between the vector kernels): one host synchronisation per
+// inner step -- the convergence test the reference makes there -- instead of one per dot product (k + 3 of them).
 int idrs(Solver& S, double* x, const double* b, double* r, double tol, int maxiter, int s, uint64_t seed, int pass,
          std::vector<double*>& W, int* iters) {
     mfb_ctx* ctx = S.ctx;
@@ -730,78 +775,77 @@ int idrs(Solver& S, double* x, const double* b, double* r, double tol, int maxit
         MFB_CUDA(cudaMemsetAsync(U[k], 0, n * sizeof(double), ctx->stream));
         MFB_CUDA(cudaMemsetAsync(G[k], 0, n * sizeof(double), ctx->stream));
     }
-    std::vector<double> M(s * s, 0.0), f(s, 0.0), c(s, 0.0);
-    for (int i = 0; i < s; ++i) M[i * s + i] = 1.0;  // M[i][k] row-major
-    double omega = 1.0;
-    std::vector<const double*> xs(2 * s + 2), ys(s + 2);
+    MFB_CUDA(ctx->ksc.alloc(SC_COUNT > 8 + 3 * MAXD + MAXD * MAXD ? SC_COUNT : 8 + 3 * MAXD + MAXD * MAXD));
+    double* sc = ctx->ksc.p;
+    const double* red = ctx->scal.p;
+    const double* cdev = sc + ID_F + s;          // c[i]
+    const double* ocdev = sc + ID_F + 2 * s;     // -omega * c[i]
+    LAUNCH(k_idr_init, 1, 128, sc, s);
+    std::vector<const double*> xs(2 * s + 2), ys(s + 2), cp(2 * s + 2);
     std::vector<double> cf(2 * s + 2);
+    auto check = [&](double* resout) -> int {    // ||r||^2 is in ctx->scal[0]
+        MFB_CUDA(cudaMemcpyAsync(ctx->h_scal, ctx->scal.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+        *resout = S.nn(ctx->h_scal[0]);
+        return MFB_OK;
+    };
     while (true) {
         for (int i = 0; i < s; ++i) { xs[i] = P[i]; ys[i] = r; }
-        MFB_TRY(S.dots(s, xs.data(), ys.data()));
-        for (int i = 0; i < s; ++i) f[i] = ctx->h_scal[i];
+        MFB_TRY(S.dots_dev(s, xs.data(), ys.data()));
+        LAUNCH(k_idr_f, 1, 32, sc, red, s);
         for (int k = 0; k < s; ++k) {
-            // c = LowerTriangular(M[k:s,k:s]) \ f[k:s]
-            for (int i = k; i < s; ++i) {
-                double v = f[i];
-                for (int j = k; j < i; ++j) v -= M[i * s + j] * c[j];
-                c[i] = v / M[i * s + i];
-            }
-            // U[k] = sum c_i U[i] + omega*(r - sum c_i G[i])
+            LAUNCH(k_idr_c, 1, 1, sc, k, s);
+            // U[k] = c_k U[k] + sum_{i>k} c_i U[i] + omega*(r - sum_{i>=k} c_i G[i])
             int nt = 0;
             for (int i = k; i < s; ++i) {
-                if (i != k) { cf[nt] = c[i]; xs[nt++] = U[i]; }
-                cf[nt] = -omega * c[i]; xs[nt++] = G[i];
+                if (i != k) { cf[nt] = 1.0; cp[nt] = cdev + i; xs[nt++] = U[i]; }
+                cf[nt] = 1.0; cp[nt] = ocdev + i; xs[nt++] = G[i];
             }
-            cf[nt] = omega; xs[nt++] = r;
-            MFB_TRY(S.lincomb(U[k], c[k], nt, cf.data(), xs.data()));
+            cf[nt] = 1.0; cp[nt] = sc + ID_OMEGA; xs[nt++] = r;
+            MFB_TRY(S.lincomb_dev(U[k], 1.0, nt, cf.data(), cp.data(), xs.data(), false, cdev + k));
             MFB_TRY(S.mul(G[k], U[k]));
             for (int i = 0; i < k; ++i) {
-                double d;
-                MFB_TRY(S.dot1(P[i], G[k], &d));
-                double alpha = d / M[i * s + i];
+                const double* dx1[1] = {P[i]};
+                const double* dy1[1] = {G[k]};
+                MFB_TRY(S.dots_dev(1, dx1, dy1));
+                LAUNCH(k_idr_alpha, 1, 1, sc, red, i, s);
                 double* yy[2] = {G[k], U[k]};
-                double a[2] = {1.0, 1.0}, bb[2] = {-alpha, -alpha};
+                const double a[2] = {1.0, 1.0}, bb[2] = {-1.0, -1.0};
+                const double* ap[2] = {nullptr, nullptr};
+                const double* bp[2] = {sc + ID_ALPHA, sc + ID_ALPHA};
                 const double* xx[2] = {G[i], U[i]};
-                MFB_TRY(S.axpby_batch(2, yy, a, bb, xx));
+                MFB_TRY(S.axpby_batch_dev(2, yy, a, ap, bb, bp, xx));
             }
             for (int i = k; i < s; ++i) { xs[i - k] = P[i]; ys[i - k] = G[k]; }
-            MFB_TRY(S.dots(s - k, xs.data(), ys.data()));
-            for (int i = k; i < s; ++i) M[i * s + k] = ctx->h_scal[i - k];
-            double beta = f[k] / M[k * s + k];
+            MFB_TRY(S.dots_dev(s - k, xs.data(), ys.data()));
+            LAUNCH(k_idr_M, 1, 1, sc, red, k, s);
             {
-                double one = beta;
-                const double* xx[1] = {U[k]};
-                MFB_TRY(S.lincomb(x, 1.0, 1, &one, xx));
-                double mb = -beta, n2;
-                const double* gg[1] = {G[k]};
-                MFB_TRY(S.lincomb(r, 1.0, 1, &mb, gg, &n2));
-                res = S.nn(n2);
+                const double one = 1.0, mone = -1.0;
+                const double* bptr[1] = {sc + ID_BETA};
+                const double* ux[1] = {U[k]};
+                const double* gx[1] = {G[k]};
+                MFB_TRY(S.lincomb_dev(x, 1.0, 1, &one, bptr, ux));
+                MFB_TRY(S.lincomb_dev(r, 1.0, 1, &mone, bptr, gx, true));
+                MFB_TRY(check(&res));
             }
-            if (res <= tol || iter >= maxiter) { *iters = iter; return MFB_OK; }
-            for (int i = k + 1; i < s; ++i) f[i] -= beta * M[i * s + k];
+            if (!(res > tol) || iter >= maxiter) { *iters = iter; return MFB_OK; }
             iter++;
         }
         MFB_TRY(S.mul(Ar, r));
         {
             const double* a3[3] = {Ar, r, Ar};
             const double* b3[3] = {Ar, r, r};
-            MFB_TRY(S.dots(3, a3, b3));
-            double n1 = std::sqrt(ctx->h_scal[0]), n2 = std::sqrt(ctx->h_scal[1]), d = ctx->h_scal[2];
-            const double angle = std::sqrt(2.0) / 2;
-            double rho = std::fabs(d / (n1 * n2));
-            omega = d / (n1 * n1);
-            if (rho < angle) omega = omega * angle / rho;
+            MFB_TRY(S.dots_dev(3, a3, b3));
+            LAUNCH(k_idr_omega, 1, 1, sc, red);
+            const double one = 1.0, mone = -1.0;
+            const double* optr[1] = {sc + ID_OMEGA};
+            const double* rx[1] = {r};
+            const double* ax[1] = {Ar};
+            MFB_TRY(S.lincomb_dev(x, 1.0, 1, &one, optr, rx));
+            MFB_TRY(S.lincomb_dev(r, 1.0, 1, &mone, optr, ax, true));
+            MFB_TRY(check(&res));
         }
-        {
-            double om = omega, n2;
-            const double* xx[1] = {r};
-            MFB_TRY(S.lincomb(x, 1.0, 1, &om, xx));
-            double mo = -omega;
-            const double* aa[1] = {Ar};
-            MFB_TRY(S.lincomb(r, 1.0, 1, &mo, aa, &n2));
-            res = S.nn(n2);
-        }
-        if (res <= tol || iter >= maxiter) { *iters = iter; return MFB_OK; }
+        if (!(res > tol) || iter >= maxiter) { *iters = iter; return MFB_OK; }
         iter++;
     }
 }
