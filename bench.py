@@ -36,7 +36,7 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--assembly-only", action="store_true", help="development aid: skip the Krylov solve in every step "
                                                                 "(prints timings of the assembly only; never a bench value)")
-    p.add_argument("--workload", default="neo_hookean", choices=["neo_hookean", "linear_elasticity", "thermo_elasticity", "j2"],
+    p.add_argument("--workload", default="neo_hookean", choices=["neo_hookean", "linear_elasticity", "thermo_elasticity", "j2", "j2_fused"],
                    help="development aid with --assembly-only: time the assembly of another BASELINE config (box side from --box)")
     p.add_argument("--spmv-sweep", action="store_true", help="development aid: time the SpMV tuning variants on the assembled "
                                                              "matrix and exit")
@@ -231,7 +231,8 @@ def main():
     spec = {"neo_hookean": lambda: wf.neo_hookean(fixed_bg=1, traction_bg=2),
             "linear_elasticity": lambda: wf.linear_elasticity(0.5769, 0.3846, 1000.0, fixed_bg=1, traction_bgs=((2, "sl"),)),
             "thermo_elasticity": lambda: wf.thermo_elasticity(fixed_bg=1, thermal_bg=2),
-            "j2": lambda: wf.j2_plasticity(fixed_bg=1, traction_bg=2)}[args.workload]()
+            "j2": lambda: wf.j2_plasticity(fixed_bg=1, traction_bg=2),
+            "j2_fused": lambda: wf.j2_plasticity(fixed_bg=1, traction_bg=2, fused=True)}[args.workload]()
     ndof_global = len(spec["basic_vars"]) * gtables.variable_size
     gstate = initial_state(gtables.x, 1.0 / n)
     if world > 1:
@@ -263,15 +264,17 @@ def main():
     elif args.workload == "thermo_elasticity":
         fd.controlpoints["T"][:] = 20.0 * np.cos(tables.x[1])
         fd.controlpoints["Te"][:] = 300.0
-    elif args.workload == "j2":
+    elif args.workload in ("j2", "j2_fused"):
         fd.controlpoints["sl1"][:] = 120.0
     else:
         fd.controlpoints["sl1"][:] = 0.01
     fd.globalfield.converge_tol = TOL
     m.assemble_Global_Variables(fd)
     m.compile_Updater_GPU(1, fd)
-    if args.workload == "j2":
+    if args.workload in ("j2", "j2_fused"):
+        fd.global_vars.update({g: 0.0 for g in spec["globals"]})
         j2 = m.api.J2MaterialState(fd, Y_initial=100.0, lam=0.0, mu=50e3, Eb=12.5e3, Ep=25e3, f_res=1.0)
+        fd.sync_fields()
     gf, td = fd.globalfield, fd.time_discretization
     m.api.update_Time(gf, td)
     ndof, nnz = gf.basicfield_size, gf.nnz

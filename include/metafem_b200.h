@@ -200,6 +200,11 @@ int mfb_j2_init(mfb_ctx *ctx, const char *prefix, double Y_initial, const char *
                 const char *const *ep_names);
 int mfb_j2_iterate_stress(mfb_ctx *ctx, const char *prefix, const mfb_j2_params *params, int64_t *n_yielded);
 int mfb_j2_update_states(mfb_ctx *ctx, const char *prefix);
+/* Fused variant: when the emitter inlines the return map into the residual kernel (descriptor: no eval_kernel, qp_in_names =
+ * committed state "<prefix>.ep1..6, .b1..6, .Y", qp_out_names = ep outputs, "<prefix>.b_eval1..6", ".Y_eval", ".count";
+ * parameters as GLOBAL_VARs "<prefix>_lam, _mu, _Eb, _Ep, _fres"), mfb_eval_qp_args / mfb_j2_iterate_stress are not needed;
+ * this returns the number of points that yielded in the last mfb_assemble_nonlinear. */
+int mfb_j2_yield_count(mfb_ctx *ctx, const char *prefix, int64_t *n_yielded);
 
 /* ---- linear algebra ---------------------------------------------------------------------
  * y = K * x in reference numbering (mul!, src/misc/04_GPU_Utils.jl:131). */

@@ -192,17 +192,41 @@ class J2MaterialState:
     def __init__(self, fem_domain, Y_initial, lam, mu, Eb, Ep, f_res, prefix="j2", func="strain_updater"):
         self.dom, self.prefix, self.Y_initial = fem_domain, prefix, float(Y_initial)
         self.lam, self.mu, self.Eb, self.Ep, self.f_res = lam, mu, Eb, Ep, f_res
-        self.n_yielded = 0
         call = next(c for b in fem_domain.spec["blocks"] for c in b.get("qp_calls", []) if c["func"] == func)
-        self._e = (C.c_char_p * 6)(*[n.encode() for n in call["arg_names"]])
+        self.fused = bool(call.get("builtin"))   # the return map is inlined in the residual kernel (weak form built with fused=True)
+        if self.fused:
+            self.prefix = prefix = call["prefix"]
+        self._e = (C.c_char_p * 6)(*[n.encode() for n in (call["outs"] if self.fused else call["arg_names"])])
         self._ep = (C.c_char_p * 6)(*[n.encode() for n in call["outs"]])
+        self._n_yielded = 0
         self.reset()
+        self.sync_params()
+
+    def sync_params(self):
+        if self.fused:
+            p = self.prefix
+            self.dom.global_vars.update({f"{p}_lam": self.lam, f"{p}_mu": self.mu, f"{p}_Eb": self.Eb, f"{p}_Ep": self.Ep,
+                                         f"{p}_fres": self.f_res})
+
+    @property
+    def n_yielded(self):
+        if self.fused:
+            n = C.c_int64(0)
+            self.dom.ctx.call("mfb_j2_yield_count", self.prefix.encode(), C.byref(n))
+            return n.value
+        return self._n_yielded
+
+    @n_yielded.setter
+    def n_yielded(self, v):
+        self._n_yielded = v
 
     def reset(self):
         """ep .= 0; b .= 0; Y .= Y_initial (J2Plasticity.jl:256-262)."""
         self.dom.ctx.call("mfb_j2_init", self.prefix.encode(), self.Y_initial, self._e, self._ep)
 
     def __call__(self, fem_domain=None, call=None):
+        if self.fused:
+            return
         prm = L.J2Params(self.lam, self.mu, self.Eb, self.Ep, self.f_res)
         n = C.c_int64(0)
         self.dom.ctx.call("mfb_j2_iterate_stress", self.prefix.encode(), C.byref(prm), C.byref(n))
@@ -340,7 +364,13 @@ def compile_Updater_GPU(domain_ID, fem_domain, tpb=128):
         kp = _f64(time_discretization.K_params)
         gf = fem_domain.globalfield
         fem_domain.sync_fields()
-        calls = [c for b in fem_domain.spec["blocks"] for c in b.get("qp_calls", [])]
+        all_calls = [c for b in fem_domain.spec["blocks"] for c in b.get("qp_calls", [])]
+        for c in all_calls:
+            if c.get("builtin"):                 # fused built-in callback: only its parameters travel (as GLOBAL_VARs)
+                fem_domain.callbacks[c["func"]].sync_params()
+        if any(c.get("builtin") for c in all_calls):
+            fem_domain.sync_fields()
+        calls = [c for c in all_calls if not c.get("builtin")]
         if calls:
             # two-phase update: argument arrays -> Main.<func> on whole arrays -> residual (08_Tensor.jl:175-183,210)
             fem_domain.ctx.call("mfb_eval_qp_args", gf.t, gf.dt)

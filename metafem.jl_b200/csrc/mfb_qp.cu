@@ -26,49 +26,10 @@ struct J2Ptrs {
 __global__ void k_j2_iterate(J2Ptrs P, mfb_j2_params m, int64_t n, unsigned long long* n_yielded) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    // assemble_strain (:103-112): Voigt slots of the six arguments
-    double et[6] = {P.e[0][i], P.e[3][i], P.e[5][i], P.e[4][i], P.e[2][i], P.e[1][i]};
-    double ep[6], b[6], s[6];
+    double ea[6], ep0[6], b0[6], ep[6], b[6], Yn;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { ep[k] = P.ep[k][i]; b[k] = P.b[k][i]; }
-    const double Y = P.Y[i];
-    // estimate_stress (:114-126) on e_test - ep
-    double ee[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) ee[k] = et[k] - ep[k];
-    const double tr = (ee[0] + ee[1]) + ee[2];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) s[k] = (2 * m.mu) * ee[k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) s[k] += m.lambda * tr;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) s[k] -= b[k];
-    const double skk = ((s[0] + s[1]) + s[2]) / 3;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) s[k] -= skk;
-    // sum over all (i, j): off-diagonal Voigt slots count twice (:153-155)
-    double s2 = 0.0;
-#pragma unroll
-    for (int ii = 0; ii < 3; ++ii)
-#pragma unroll
-        for (int jj = 0; jj < 3; ++jj) {
-            const int v = ii == jj ? ii : (ii + jj == 3 ? 3 : (ii + jj == 2 ? 4 : 5));   // (2,3)->4th, (1,3)->5th, (1,2)->6th
-            s2 += s[v] * s[v];
-        }
-    const double mag = sqrt(s2);
-    const double f = sqrt(3.0 / 2.0) * mag - Y;
-    double Yn = Y;
-    if (f > m.f_res) {
-        const double lp = sqrt(3.0 / 2.0) * f / (3 * m.mu + m.Eb + m.Ep);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            const double nd = s[k] / mag;
-            ep[k] = ep[k] + nd * lp;
-            b[k] = b[k] + (2.0 / 3.0 * m.Eb) * nd * lp;
-        }
-        Yn = Y + (sqrt(2.0 / 3.0) * m.Ep) * lp;
-        atomicAdd(n_yielded, 1ULL);
-    }
+    for (int k = 0; k < 6; ++k) { ea[k] = P.e[k][i]; ep0[k] = P.ep[k][i]; b0[k] = P.b[k][i]; }
+    if (mfb::j2_return_map(ea, ep0, b0, P.Y[i], m.lambda, m.mu, m.Eb, m.Ep, m.f_res, ep, b, Yn)) atomicAdd(n_yielded, 1ULL);
 #pragma unroll
     for (int k = 0; k < 6; ++k) { P.ep_eval[k][i] = ep[k]; P.b_eval[k][i] = b[k]; }
     P.Y_eval[i] = Yn;
@@ -207,5 +168,19 @@ extern "C" int mfb_j2_update_states(mfb_ctx* ctx, const char* prefix) {
     MFB_TRY(mfb_qp_lookup(ctx, j2name(prefix, "Y_eval", -1), &src));
     MFB_TRY(mfb_qp_lookup(ctx, j2name(prefix, "Y", -1), &dst));
     MFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return MFB_OK;
+}
+
+// Fused path (the return map is inlined in the element kernel): number of points that yielded in the last
+// mfb_assemble_nonlinear; the counter is the first word of the integration-point array "<prefix>.count".
+extern "C" int mfb_j2_yield_count(mfb_ctx* ctx, const char* prefix, int64_t* n_yielded) {
+    if (!ctx || !prefix || !n_yielded) return MFB_ERR_ARG;
+    MFB_CUDA(cudaSetDevice(ctx->device));
+    double* p = nullptr;
+    MFB_TRY(mfb_qp_lookup(ctx, std::string(prefix) + ".count", &p));
+    unsigned long long h = 0;
+    MFB_CUDA(cudaMemcpyAsync(&h, p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_yielded = (int64_t)h;
     return MFB_OK;
 }

@@ -83,6 +83,53 @@ __device__ __forceinline__ double inv3(const double (&J)[3][3], double (&I)[3][3
     return det;
 }
 
+// Radial-return update of the reference's J2 example (iterate_stress!, examples/hypo_elastic_plasticity/J2Plasticity.jl:118-188)
+// for ONE quadrature point. e_arg: the callback's arguments e11 e12 e13 e22 e23 e33; ep, b, Y: committed state (Voigt order
+// 11 22 33 23 13 12); outputs: the trial state ep_eval, b_eval, Y_eval. Returns true if the point yielded.
+// Used by the stand-alone return-map kernel (mfb_qp.cu) and, inlined, by element kernels with a fused callback.
+__device__ __forceinline__ bool j2_return_map(const double (&e_arg)[6], const double (&ep_in)[6], const double (&b_in)[6], double Y,
+                                              double lambda, double mu, double Eb, double Ep, double f_res,
+                                              double (&ep)[6], double (&b)[6], double& Yn) {
+    // assemble_strain (:103-112): Voigt slots of the six arguments
+    const double et[6] = {e_arg[0], e_arg[3], e_arg[5], e_arg[4], e_arg[2], e_arg[1]};
+    double s[6], ee[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { ep[k] = ep_in[k]; b[k] = b_in[k]; ee[k] = et[k] - ep_in[k]; }
+    // estimate_stress (:114-126) on e_test - ep
+    const double tr = (ee[0] + ee[1]) + ee[2];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s[k] = (2 * mu) * ee[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s[k] += lambda * tr;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s[k] -= b[k];
+    const double skk = ((s[0] + s[1]) + s[2]) / 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s[k] -= skk;
+    // sum over all (i, j): off-diagonal Voigt slots count twice (:153-155)
+    double s2 = 0.0;
+#pragma unroll
+    for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) {
+            const int v = ii == jj ? ii : (ii + jj == 3 ? 3 : (ii + jj == 2 ? 4 : 5));   // (2,3)->4th, (1,3)->5th, (1,2)->6th
+            s2 += s[v] * s[v];
+        }
+    const double mag = sqrt(s2);
+    const double f = sqrt(3.0 / 2.0) * mag - Y;
+    Yn = Y;
+    if (!(f > f_res)) return false;
+    const double lp = sqrt(3.0 / 2.0) * f / (3 * mu + Eb + Ep);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const double nd = s[k] / mag;
+        ep[k] = ep[k] + nd * lp;
+        b[k] = b[k] + (2.0 / 3.0 * Eb) * nd * lp;
+    }
+    Yn = Y + (sqrt(2.0 / 3.0) * Ep) * lp;
+    return true;
+}
+
 // Form contract (emitted code):
 //   static constexpr int NV, NA, NQ, L1 (= max_time_level + 1), BOUNDARY (0/1), LINEAR (0/1),
 //                        NW (inner words), NCW (cp words), NC (cp fields), HAS_RES, HAS_K, TPB,
@@ -94,7 +141,7 @@ __device__ __forceinline__ double inv3(const double (&J)[3][3], double (&I)[3][3
 //   __device__ static constexpr int wslot(int k), wlev(int k), wpos(int k);   // inner word k: slot, time level, variable
 //   __device__ static constexpr int cslot(int k), cfield(int k);              // cp word k: slot, field index
 //   static constexpr int EVAL (0/1), NQPI (integration-point words read), NQPO (callback arguments written);
-//   __device__ static void point(const double* w, const double* c, const double* nrm, const double* qv, const MfbArgs& A,
+//   __device__ static void point(const double* w, const double* c, const double* nrm, const double* qv, size_t qidx /* q + NQ * reference element */, const MfbArgs& A,
 //                                double* R /*[NV*4], zeroed*/, double* D /*[ND], zeroed*/);   // NOT yet weighted
 //   __device__ static void qp_eval(const double* w, const double* c, const MfbArgs& A, double* out /*[NQPO]*/);  // EVAL forms:
 //        // arguments of the user callback at this quadrature point (phase A of the two-phase update, 08_Tensor.jl:175-183)
@@ -290,17 +337,18 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
                     const double wgt = S.geo.wgt[q];
                     const double nrm[3] = {S.geo.nrm[q][0], S.geo.nrm[q][1], S.geo.nrm[q][2]};
                     double qv[F::NQPI > 0 ? F::NQPI : 1];
+                    size_t qidx = 0;
                     if constexpr (F::NQPI > 0) {
-                        const size_t qbase = (size_t)A.elem_ref[e] * NQ;
+                        qidx = (size_t)A.elem_ref[e] * NQ + q;
 #pragma unroll
-                        for (int k = 0; k < F::NQPI; ++k) qv[k] = A.qpi[k][qbase + q];
+                        for (int k = 0; k < F::NQPI; ++k) qv[k] = A.qpi[k][qidx];
                     }
                     double R[NV * 4], D[F::ND > 0 ? F::ND : 1];
 #pragma unroll
                     for (int k = 0; k < NV * 4; ++k) R[k] = 0.0;
 #pragma unroll
                     for (int k = 0; k < F::ND; ++k) D[k] = 0.0;
-                    F::point(w, c, nrm, qv, A, R, D);
+                    F::point(w, c, nrm, qv, qidx, A, R, D);
 #pragma unroll
                     if constexpr (F::HAS_RES)
                         for (int k = 0; k < NV * 4; ++k) S.gu[q][k] = R[k] * wgt;       // all words of this q are in registers by now

@@ -59,6 +59,16 @@ def _form(name, spec, blk, n_a, n_q, linear, evalk=False):
         terms, residues = [], []
     qpw = [] if (linear or evalk) else [w for w in ext if w["kind"] == "qp"]
     qpo = [(a, n) for c in calls for a, n in zip(c["args"], c["arg_names"])] if evalk else []
+    fused = [c for c in calls if c.get("builtin")] if not (linear or evalk) else []
+    if len(fused) > 1 or (fused and len(fused) != len(calls)):
+        raise ValueError("one built-in quadrature-point callback per block, not mixed with user callbacks")
+    qp_in_names, qp_out_names = [w["sym"] for w in qpw], [n for _, n in qpo]
+    if fused:
+        if fused[0]["builtin"] != "j2_return_map":
+            raise ValueError(f"unknown built-in callback {fused[0]['builtin']!r}")
+        pre = fused[0]["prefix"]
+        qp_in_names = [f"{pre}.ep{k}" for k in range(1, 7)] + [f"{pre}.b{k}" for k in range(1, 7)] + [f"{pre}.Y"]
+        qp_out_names = list(fused[0]["outs"]) + [f"{pre}.b_eval{k}" for k in range(1, 7)] + [f"{pre}.Y_eval", f"{pre}.count"]
     if (qpw or qpo) and boundary:
         raise ValueError("INTEGRATION_POINT_VAR words are supported in domain blocks only")
     cpw = [w for w in ext if w["kind"] == "cp"]
@@ -79,7 +89,7 @@ def _form(name, spec, blk, n_a, n_q, linear, evalk=False):
                  f"HAS_RES = {int(bool(residues))}, HAS_K = {int(bool(terms))}, TPB = {tpb}, "
                  f"NSD = {nsd}, KS = {ks}, ND = {nd}, NTC = {tl['NTC']}, CG = {tl['CG']}, W = {tl['W']}, "
                  f"LPW = {tl['LPW']}, SMEM = @SMEM@, "
-                 f"EVAL = {int(evalk)}, NQPI = {len(qpw)}, NQPO = {len(qpo)}, NGS = {len(gslots)};")
+                 f"EVAL = {int(evalk)}, NQPI = {len(qp_in_names)}, NQPO = {len(qpo)}, NGS = {len(gslots)};")
     lines.append(_table("gslot", [gslots.index(sl) if sl in gslots else -1 for sl in range(4)]))
     lines.append(_table("gslot_id", gslots))
     lines.append(_table("dslot", dslots))
@@ -103,18 +113,32 @@ def _form(name, spec, blk, n_a, n_q, linear, evalk=False):
             lines.append(f"    out[{k}] = {a};")
         lines.append("  }")
     lines.append("  __device__ static __forceinline__ void point(const double* w, const double* c, const double* nrm, "
-                 "const double* qv, const MfbArgs& A, double* R, double* D) {")
+                 "const double* qv, size_t qidx, const MfbArgs& A, double* R, double* D) {")
     for k, w in enumerate([] if evalk else inner):
         lines.append(f"    const double {w['sym']} = w[{k}];")
     for k, w in enumerate([] if evalk else cpw):
         lines.append(f"    const double {w['sym']} = c[{k}];")
-    for k, w in enumerate(qpw):
+    for k, w in enumerate([] if fused else qpw):
         lines.append(f"    const double {w['sym']} = qv[{k}];")
     for w in ([] if evalk else ext):
         if w["kind"] == "normal":
             lines.append(f"    const double {w['sym']} = nrm[{w['c'] - 1}];")
         elif w["kind"] == "global":
             lines.append(f"    const double {w['sym']} = A.glob[{globs.index(w['sym'])}];")
+    if fused:
+        # the library's radial return inlined (reference: the MaterialState callable of J2Plasticity.jl:97-188)
+        c0, pre = fused[0], fused[0]["prefix"]
+        lines.append("    const double j2_e[6] = {" + ", ".join(c0["args"]) + "};")
+        lines.append("    const double j2_ep0[6] = {qv[0], qv[1], qv[2], qv[3], qv[4], qv[5]};")
+        lines.append("    const double j2_b0[6] = {qv[6], qv[7], qv[8], qv[9], qv[10], qv[11]};")
+        lines.append("    double j2_ep[6], j2_b[6], j2_Y;")
+        lines.append(f"    if (mfb::j2_return_map(j2_e, j2_ep0, j2_b0, qv[12], {pre}_lam, {pre}_mu, {pre}_Eb, {pre}_Ep, {pre}_fres, "
+                     "j2_ep, j2_b, j2_Y))")
+        lines.append("      atomicAdd(reinterpret_cast<unsigned long long*>(A.qpo[13]), 1ull);")
+        lines.append("    for (int k = 0; k < 6; ++k) { A.qpo[k][qidx] = j2_ep[k]; A.qpo[6 + k][qidx] = j2_b[k]; }")
+        lines.append("    A.qpo[12][qidx] = j2_Y;")
+        for k, o in enumerate(c0["outs"]):
+            lines.append(f"    const double {o} = j2_ep[{k}];")
     known = {w["sym"] for w in inner} | {w["sym"] for w in ext}
     ident = re.compile(r"[A-Za-z_][A-Za-z_0-9]*")
     for t in ([] if evalk else blk["temps"]):
@@ -142,7 +166,7 @@ def _form(name, spec, blk, n_a, n_q, linear, evalk=False):
     smem = _align16(_align16(max(gd, ke)) + geo + 8 * (n_q * 4 * max(nvl, 1) + n_a * 3 + L1 * n_a * nv
                                                       + max(len(fields), 1) * n_a) + 4 * n_a)
     body = "\n".join(lines).replace("@SMEM@", str(smem))
-    return body, fields, globs, smem, bool(terms), tpb, [w["sym"] for w in qpw], [n for _, n in qpo]
+    return body, fields, globs, smem, bool(terms), tpb, qp_in_names, qp_out_names
 
 
 def _is_number(s):
@@ -178,7 +202,7 @@ def emit(spec, n_a, n_q, n_qb, tpb=None):
             variants.append(("lin", True))
         if blk["residues"] or blk["nonlinear_gradients"]:
             variants.append(("nl", False))
-        if blk.get("qp_calls"):
+        if any(not c.get("builtin") for c in blk.get("qp_calls", [])):
             variants.append(("ev", False))
         forms = {tag: _form(f"F_b{i}_{tag}", spec, blk, n_a, nq, lin, evalk=(tag == "ev")) for tag, lin in variants}
         # both kernels of a block are launched with the same shape
@@ -193,6 +217,8 @@ def emit(spec, n_a, n_q, n_qb, tpb=None):
             if tag == "nl":
                 d["has_nonlinear_K"] = int(hask)
                 d["qp_in_names"] = qpin
+                if qpout:                       # fused built-in callback: the residual kernel writes the trial state
+                    d["qp_out_names"] = qpout
             if tag == "ev":
                 d["qp_out_names"] = qpout
         d["threads_per_block"] = block_tpb

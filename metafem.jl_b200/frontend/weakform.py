@@ -100,13 +100,18 @@ class Physics:
         self.glob[s] = name
         return s
 
-    def qpcall(self, func, args, out_names):
+    def qpcall(self, func, args, out_names, builtin=None, prefix=None):
         """``outs = Main.func(args...)`` evaluated on whole [n_q, n_el] arrays (08_Tensor.jl:175-183,210); the outputs
         are external INTEGRATION_POINT_VAR words: zero variation (09_Differentiation.jl:68-69)."""
         outs = [sp.Symbol(n, real=True) for n in out_names]
         for o in outs:
             self.qp[o] = o.name
-        self.qp_calls.append(dict(func=func, args=[sp.sympify(a) for a in args], outs=outs))
+        # builtin = "j2_return_map": the library's radial-return update is inlined into the residual kernel instead of
+        # calling back (state arrays "<prefix>.*", parameters as GLOBAL_VARs "<prefix>_lam, _mu, _Eb, _Ep, _fres")
+        self.qp_calls.append(dict(func=func, args=[sp.sympify(a) for a in args], outs=outs, builtin=builtin, prefix=prefix))
+        if builtin:
+            for g in ("lam", "mu", "Eb", "Ep", "fres"):
+                self.g(f"{prefix}_{g}")
         return outs
 
     def form(self, kind, bg_ID=0):
@@ -159,7 +164,9 @@ class Physics:
                         used |= a.free_symbols
                     calls.append(dict(func=c["func"], args=[cexpr(a) for a in c["args"]],
                                       arg_names=[f"{c['func']}_arg{k + 1}" for k in range(len(c["args"]))],
-                                      outs=[o.name for o in c["outs"]]))
+                                      outs=[o.name for o in c["outs"]], builtin=c["builtin"], prefix=c["prefix"]))
+                    if c["builtin"]:
+                        used |= {sym for sym, nm in self.glob.items() if nm.startswith(c["prefix"] + "_")}
             inner = [dict(sym=s.name, pos=pos[self.inner[s][0]], td=self.inner[s][1], sd=list(self.inner[s][2]))
                      for s in sorted((s for s in used if s in self.inner), key=lambda s: s.name)]
             ext = []
@@ -303,7 +310,7 @@ def thermo_elasticity(E=210e3, nu=0.0, tau_b=None, rho=1e3, c=0.01, h=100.0, C=1
     return P.spec()
 
 
-def j2_plasticity(E=100e3, nu=0.0, rho=1e3, c=2.0, tau_b=None, L_box=1.0, fixed_bg=1, traction_bg=2):
+def j2_plasticity(E=100e3, nu=0.0, rho=1e3, c=2.0, tau_b=None, L_box=1.0, fixed_bg=1, traction_bg=2, fused=False):
     """examples/hypo_elastic_plasticity/J2Plasticity.jl:44-63: small-strain J2 flow with the plastic strain ``ep`` an
     INTEGRATION_POINT_VAR produced by the user callback ``strain_updater`` (the return map, :118-198); second time
     derivatives (max_time_level = 2). ``ep`` has zero variation, so the tangent is the constant elastic one and lands
@@ -314,8 +321,9 @@ def j2_plasticity(E=100e3, nu=0.0, rho=1e3, c=2.0, tau_b=None, L_box=1.0, fixed_
     gd = [[P.u(f"d{i}", 0, (j,)) for j in (1, 2, 3)] for i in (1, 2, 3)]
     e = [[(gd[i][j] + gd[j][i]) / 2 for j in range(3)] for i in range(3)]
     # ep{i,j} = strain_updater(e{1,1}, e{1,2}, e{1,3}, e{2,2}, e{2,3}, e{3,3}); six outputs in Voigt order (08_Tensor.jl:160)
+    # fused = True: the callback is the library's built-in return map, inlined into the residual kernel (no two-phase update)
     epv = P.qpcall("strain_updater", [e[0][0], e[0][1], e[0][2], e[1][1], e[1][2], e[2][2]],
-                   [f"ep{k}" for k in range(1, 7)])
+                   [f"ep{k}" for k in range(1, 7)], builtin="j2_return_map" if fused else None, prefix="j2" if fused else None)
     ep = [[epv[_VOIGT[(i + 1, j + 1)] - 1] for j in range(3)] for i in range(3)]
     ee = [[e[i][j] - ep[i][j] for j in range(3)] for i in range(3)]
     tr = ee[0][0] + ee[1][1] + ee[2][2]

@@ -74,6 +74,7 @@ _SIGS = {
     "mfb_j2_init": (C.c_int, [_P, C.c_char_p, C.c_double, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]),
     "mfb_j2_iterate_stress": (C.c_int, [_P, C.c_char_p, C.POINTER(J2Params), C.POINTER(C.c_int64)]),
     "mfb_j2_update_states": (C.c_int, [_P, C.c_char_p]),
+    "mfb_j2_yield_count": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64)]),
     "mfb_spmv": (C.c_int, [_P, C.c_int, _P, _P, C.c_int64]),
     "mfb_spmv_variant_bench": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mfb_krylov_solve": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64, _P,

@@ -53,6 +53,8 @@ def spec_for(name):
         return wf.thermo_elasticity(fixed_bg=1, thermal_bg=3)
     if name == "j2":
         return wf.j2_plasticity(fixed_bg=1, traction_bg=2)
+    if name == "j2_fused":
+        return wf.j2_plasticity(fixed_bg=1, traction_bg=2, fused=True)
     raise KeyError(name)
 
 
@@ -89,7 +91,7 @@ def build_case(name, n=(3, 2, 2), size=(1.5, 1.0, 1.0), seed=0):
             dom.cp[b + "_t1"][:] = 1e-4 * mesh.x[(i + 2) % 3]
         dom.globalfield.dt = 1.0
         dom.globalfield.converge_tol = 1e-6
-    elif name == "j2":
+    elif name in ("j2", "j2_fused"):
         # strains around 1e-3: part of the quadrature points are beyond the yield surface (Y = 100, E = 1e5)
         for i, b in enumerate(("d1", "d2", "d3")):
             dom.cp[b][:] = 4e-4 * np.sin(1.3 * mesh.x[(i + 1) % 3] + 0.2 * i) * mesh.x[0] + rng.uniform(-1e-5, 1e-5, N) * h
@@ -140,6 +142,7 @@ def j2_states(dom, fd=None):
     pst = None
     if fd is not None:
         import metafem_b200 as m
+        fd.global_vars.update({g: 0.0 for g in fd.spec["globals"]})     # the material state fills its own parameters
         pst = m.api.J2MaterialState(fd, **J2_PARAMS)
         fd.callbacks["strain_updater"] = pst
     return ost, pst

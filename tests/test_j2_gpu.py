@@ -9,10 +9,11 @@ from oracle import assembly as oasm, solver as osv
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def pair(built_lib):
+@pytest.fixture(scope="module", params=["j2", "j2_fused"])
+def pair(request, built_lib):
+    """"j2": two-phase update around the callback; "j2_fused": the built-in return map inlined into the residual kernel."""
     import metafem_b200 as m
-    dom, spec, mesh = build_case("j2", (4, 2, 2), size=(4.0, 1.0, 1.0))
+    dom, spec, mesh = build_case(request.param, (4, 2, 2), size=(4.0, 1.0, 1.0))
     oasm.assemble_Global_Variables(dom)
     fd = product_from_oracle(dom)
     m.assemble_Global_Variables(fd)
@@ -70,6 +71,8 @@ def test_j2_argument_arrays(pair):
     """Phase A of the two-phase update fills e11 e12 e13 e22 e23 e33 at the quadrature points (reference order)."""
     import metafem_b200 as m
     dom, fd, ost, pst = pair
+    if pst.fused:
+        pytest.skip("no argument arrays when the callback is fused into the kernel")
     _assemble_both(dom, fd)
     blk = dom.spec["blocks"][0]
     cx = oasm._block_context(dom, blk)
@@ -84,6 +87,8 @@ def test_j2_host_callback_equals_builtin(pair):
     import metafem_b200 as m
     from oracle import j2 as oj2
     dom, fd, ost, pst = pair
+    if pst.fused:
+        pytest.skip("the fused kernel has no callback seam")
     fd.K_nonlinear_func(fd.time_discretization, fem_domain=fd)
     r_builtin = fd.get_vector(m.lib.VEC_RESIDUE)
     user = oj2.MaterialState(fd.qp_shape, **J2_PARAMS)
@@ -132,14 +137,15 @@ def test_j2_load_steps(pair):
     assert np.abs(pst.state("ep1") - ost.ep[0]).max() < 1e-2 * np.abs(ost.ep[0]).max()
 
 
-def test_j2_cuda_path_matches_analytical_table(built_lib):
+@pytest.mark.parametrize("case", ["j2", "j2_fused"])
+def test_j2_cuda_path_matches_analytical_table(built_lib, case):
     """The script's loading loop (J2Plasticity.jl:264-283) entirely on the CUDA path -- update_OneStep!, built-in return
     map, update_States!, dessemble_X! -- against the script's analytical load-displacement table (:223-228, group 1:
     isotropic hardening, loading into yield and partial unloading)."""
     import metafem_b200 as m
     EY = 100e3
     s_tests, d1_ana = [40, 80, 100, 120, 140, 180, 200, 180, 100], [4, 8, 10, 16, 22, 34, 40, 38, 30]
-    dom, spec, mesh = build_case("j2", (5, 2, 2), size=(10.0, 1.0, 1.0))
+    dom, spec, mesh = build_case(case, (5, 2, 2), size=(10.0, 1.0, 1.0))
     for k in dom.cp:
         dom.cp[k][:] = 0.0
     fd = product_from_oracle(dom)
