@@ -11,6 +11,8 @@
  *  - every array argument may be a device pointer, a CUDA unified pointer (the reference's
  *    default array type, src/misc/04_GPU_Utils.jl:8) or a plain/pinned host pointer; host
  *    buffers are staged through the context's stream inside the call;
+ *  - small parameter vectors (K_params, alpha/beta/gamma_params, sparse_mapping, el_cp_outer_id, name lists) and all
+ *    output scalars are HOST pointers;
  *  - the library borrows caller memory only for the duration of a call;
  *  - every function returns MFB_OK (0) or a negative error code; mfb_last_error() gives text.
  *    MFB_NOT_CONVERGED (1) is a warning: results are valid, the reference only prints in that

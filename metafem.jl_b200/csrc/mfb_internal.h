@@ -34,10 +34,20 @@
         if (_s < 0) return _s;        \
     } while (0)
 
+// Owning device buffer: released on scope exit (also on the early returns of MFB_TRY / MFB_CUDA), move-only.
 template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
     cudaError_t alloc(size_t count) {
         if (count == n && p) return cudaSuccess;
         release();
