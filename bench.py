@@ -40,6 +40,8 @@ def parse():
                    help="development aid with --assembly-only: time the assembly of another BASELINE config (box side from --box)")
     p.add_argument("--spmv-sweep", action="store_true", help="development aid: time the SpMV tuning variants on the assembled "
                                                              "matrix and exit")
+    p.add_argument("--detail-timers", action="store_true", help="also time every Krylov reduction group and interface exchange "
+                                                                "(perturbs the stream; diagnosis only)")
     p.add_argument("--ncu", action="store_true", help="profiler capture run: exactly W warm-up steps, no e2e pass; "
                                                       "numbers printed by such a run are never bench values")
     return p.parse_args()
@@ -352,7 +354,7 @@ def main():
     clocks = ClockSampler(local)
     clocks.start()
     l0 = fd.ctx.lib.mfb_launch_count(fd.ctx.h)
-    fd.ctx.call("mfb_profile_enable", 1)
+    fd.ctx.call("mfb_profile_enable", 2 if args.detail_timers else 1)
     ms_total = timed(False, K)
     launches = fd.ctx.lib.mfb_launch_count(fd.ctx.h) - l0
     pms = (C.c_double * 8)(); pcnt = (C.c_int64 * 8)()
@@ -398,7 +400,8 @@ def main():
         "newton_step_ms": ms_step, "assembly_ms": asm_ms, "assembly_dof_per_s": ndof_global / (asm_ms * 1e-3),
         "element_kernel_ms": elem_ms, "solve_ms": pms[3] / max(pcnt[3], 1), "spmv_ms": spmv_ms,
         "spmv_share_of_step": pms[0] / ms_total,
-        "halo_exchange_ms_per_step": pms[5] / K, "krylov_reductions_ms_per_step": pms[6] / K,
+        "halo_exchange_ms_per_step": pms[5] / K if args.detail_timers else None,
+        "krylov_reductions_ms_per_step": pms[6] / K if args.detail_timers else None,
         "roofline": {"bound": "hbm", "kernel": "k_spmv_bsr<3>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": spmv_traffic if world == 1 else None, "traffic_source": spmv_src,
                      "peak_kind": peak_kind,

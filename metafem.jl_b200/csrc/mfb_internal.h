@@ -82,6 +82,9 @@ enum { MFB_T_SPMV = 0, MFB_T_ASM_NONLINEAR = 1, MFB_T_ASM_LINEAR = 2, MFB_T_SOLV
 struct ProfEvents {
     std::vector<cudaEvent_t> start, stop;
 };
+// fine-grained timers (one pair of events per reduction group / interface exchange) perturb the stream they measure:
+// they are recorded only at profile level 2
+inline bool mfb_prof_detail(int id) { return id == 5 || id == 6; }
 
 struct mfb_ctx {
     int device = 0;
@@ -149,6 +152,8 @@ struct mfb_ctx {
 
     // ---- profiling ----
     bool profile = false;
+    int profile_level = 1;
+    std::vector<cudaEvent_t> event_pool;   // recycled by mfb_profile_get
     ProfEvents prof[MFB_T_COUNT];
     double prof_ms[MFB_T_COUNT] = {0};
     int64_t prof_n[MFB_T_COUNT] = {0};
@@ -158,17 +163,21 @@ struct ProfScope {
     mfb_ctx* c;
     int id;
     bool on;
-    ProfScope(mfb_ctx* ctx, int id_) : c(ctx), id(id_), on(ctx->profile) {
-        if (!on) return;
+    static cudaEvent_t get(mfb_ctx* c) {
         cudaEvent_t e;
-        cudaEventCreate(&e);
+        if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    }
+    ProfScope(mfb_ctx* ctx, int id_) : c(ctx), id(id_), on(ctx->profile && (ctx->profile_level >= 2 || !mfb_prof_detail(id_))) {
+        if (!on) return;
+        cudaEvent_t e = get(c);
         cudaEventRecord(e, c->stream);
         c->prof[id].start.push_back(e);
     }
     ~ProfScope() {
         if (!on) return;
-        cudaEvent_t e;
-        cudaEventCreate(&e);
+        cudaEvent_t e = get(c);
         cudaEventRecord(e, c->stream);
         c->prof[id].stop.push_back(e);
     }

@@ -21,7 +21,8 @@
 namespace {
 
 constexpr int TPB = 256;
-constexpr int MAXT = 64;   // max terms of one fused vector update
+constexpr int MAXT = 48;   // max terms of one fused linear combination (idrs! needs 2 s + 1)
+constexpr int MAXB = 24;   // max independent updates of one batched axpby (bicgstabl needs s + 2)
 constexpr int MAXD = 24;   // max dots of one fused reduction
 constexpr int RED_BLOCKS = 1184;  // 8 x 148 SMs, 256 threads each
 
@@ -347,7 +348,7 @@ struct LinComb {
 // optional fused squared norm of the result (partials[block]); 4 independent elements per thread for memory-level parallelism
 __global__ void __launch_bounds__(TPB) k_lincomb(LinComb L, int64_t n, double* partial_norm2, const unsigned char* owned, int nv) {
     double nrm = 0.0;
-    if (L.ayp) L.ay *= __ldg(L.ayp);
+    const double ay = L.ayp ? L.ay * __ldg(L.ayp) : L.ay;     // (never write to the by-value parameter struct: that would spill all of it to local memory)
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
         double sv[4];
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(TPB) k_lincomb(LinComb L, int64_t n, double* p
         for (int u = 0; u < 4; ++u) {
             idx[u] = i0 + u * stride;
             if (idx[u] >= n) idx[u] = -1;
-            sv[u] = (L.ay != 0.0 && idx[u] >= 0) ? L.ay * L.y[idx[u]] : 0.0;
+            sv[u] = (ay != 0.0 && idx[u] >= 0) ? ay * L.y[idx[u]] : 0.0;
         }
         for (int k = 0; k < L.n; ++k) {
             const double c = L.cp[k] ? L.c[k] * __ldg(L.cp[k]) : L.c[k];
@@ -387,11 +388,11 @@ __global__ void __launch_bounds__(TPB) k_lincomb(LinComb L, int64_t n, double* p
 
 struct AxpbyBatch {
     int n;
-    double a[MAXT], b[MAXT];
-    double* y[MAXT];
-    const double* x[MAXT];
-    const double* ap[MAXT];   // optional device-resident factors of a_k and b_k (nullptr -> 1)
-    const double* bp[MAXT];
+    double a[MAXB], b[MAXB];
+    double* y[MAXB];
+    const double* x[MAXB];
+    const double* ap[MAXB];   // optional device-resident factors of a_k and b_k (nullptr -> 1)
+    const double* bp[MAXB];
 };
 // y_k = a_k*y_k + b_k*x_k for k < n, independent updates in one launch
 __global__ void __launch_bounds__(TPB) k_axpby_batch(AxpbyBatch Bt, int64_t n) {
@@ -1330,7 +1331,8 @@ extern "C" int mfb_krylov_solve_ex(mfb_ctx* ctx, int method, int s, int maxiter,
     MFB_REQUIRE(method >= MFB_IDRS && method <= MFB_LSQR, MFB_ERR_ARG, "unknown Krylov method");
     MFB_REQUIRE(pr_mode >= MFB_PR_JACOBI && pr_mode <= MFB_PR_IDENTITY && pl_mode >= MFB_PL_IDENTITY && pl_mode <= MFB_PL_JACOBI_ROW,
                 MFB_ERR_ARG, "unknown preconditioner mode");
-    MFB_REQUIRE(s >= 1 && (method == MFB_GMRES ? s + 1 <= MAXT : (3 * s + 4 <= MAXT && s <= MAXD)), MFB_ERR_ARG, "s out of range");
+    MFB_REQUIRE(s >= 1 && (method == MFB_GMRES ? s + 1 <= MAXT : (2 * s + 2 <= MAXT && s + 2 <= MAXB && s <= MAXD)), MFB_ERR_ARG,
+                "s out of range");
     MFB_REQUIRE(!(mfb_is_distributed(ctx) && (pr_mode == MFB_PR_JACOBI_COLUMN || pl_mode == MFB_PL_JACOBI_ROW)), MFB_ERR_ARG,
                 "row/column-norm Jacobi needs assembled rows: not available on a partitioned mesh");
     MFB_CUDA(cudaSetDevice(ctx->device));
