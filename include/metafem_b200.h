@@ -95,6 +95,28 @@ int mfb_mesh_set(mfb_ctx *ctx, int n_a, int64_t n_el, int64_t N, int n_q,
                  const int32_t *controlpoint_IDs, const double *x1, const double *x2, const double *x3,
                  const double *ref_itp_vals, const double *itg_weight);
 
+/* Second-order mesh tables from a first-order mesh, built on the device (replaces, for the hot path's inputs, the segment /
+ * face tables of construct_TotalMesh_3D -- src/mesh/ref_geometry/002_Initialization.jl:113-217 through the GPU hash of
+ * src/misc/06_GPU_Dict.jl --, get_BoundaryMesh, and the control-point allocation of mesh_Classical,
+ * src/mesh/unstructured_mesh/3_InitializeMesh.jl:70-178):
+ *   x1,x2,x3 [n_vert], connections [vpb, n_el] (1-based vertex IDs): the output of make_Brick / read_Mesh;
+ *   element-type tables (101_Structures.jl:129-196,224-247), 1-based: segment_vertices [2, n_seg], vertex_cp_ids [vpb],
+ *   segment_cp_ids [n_seg] (control-point slot of each vertex / segment), face_vertices [vpf, n_faces].
+ * Control points: vertices first in input order (as the reference), then one per segment in sorted order of
+ * (max vertex, min vertex) -- deterministic and locality-preserving, where the reference's order is that of its racy hash
+ * table. Boundary facets (faces owned by one element) come in (local face, element) order with their centroids, for the
+ * script's geometric selection of boundary groups. Results stay on the device (mfb_mesh_build_device_ptrs, to be passed
+ * to mfb_mesh_set) and can be copied out (mfb_mesh_build_get; any pointer may be NULL). */
+int mfb_mesh_build_second_order(mfb_ctx *ctx, int64_t n_vert, const double *x1, const double *x2, const double *x3,
+                                int vpb, int64_t n_el, const int32_t *connections, int n_seg,
+                                const int32_t *segment_vertices, const int32_t *vertex_cp_ids,
+                                const int32_t *segment_cp_ids, int n_faces, int vpf, const int32_t *face_vertices,
+                                int64_t *n_controlpoints, int64_t *n_boundary_facets);
+int mfb_mesh_build_get(mfb_ctx *ctx, int32_t *controlpoint_IDs, double *x1, double *x2, double *x3,
+                       int32_t *bfacet_element_ID, int32_t *bfacet_element_eindex, double *bfacet_centroids);
+int mfb_mesh_build_device_ptrs(mfb_ctx *ctx, const int32_t **controlpoint_IDs, const double **x1, const double **x2,
+                               const double **x3);
+
 /* Boundary tables (4_Update_Integrator.jl:35-75; 3_InitializeMesh.jl:119-130,165-178):
  *   bdy_ref_itp_vals       [n_qb, n_a, 2, 2, 2, n_faces]   one table per local face (eindex)
  *   bdy_itg_weights        [n_qb, n_faces]

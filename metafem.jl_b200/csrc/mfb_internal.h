@@ -74,7 +74,8 @@ struct BoundaryGroup {
     int64_t n = 0;
 };
 
-struct Comm;  // mfb_dist.cu
+struct Comm;       // mfb_dist.cu
+struct MeshBuild;  // mfb_meshbuild.cu
 
 // CUDA-event timers on the context's stream (bench.py roofline numbers); ids = MFB_T_*
 enum { MFB_T_SPMV = 0, MFB_T_ASM_NONLINEAR = 1, MFB_T_ASM_LINEAR = 2, MFB_T_SOLVE = 3, MFB_T_ELEM_KERNEL = 4, MFB_T_HALO = 5,
@@ -146,6 +147,7 @@ struct mfb_ctx {
     DevBuf<unsigned char> stage;
 
     Comm* comm = nullptr;
+    MeshBuild* meshbuild = nullptr;   // tables of the last mfb_mesh_build_second_order
     DevBuf<unsigned char> owned;   // [N] internal order: 1 if this rank owns the node (all 1 on a single GPU)
     double n_global_nodes = 0;     // number of distinct nodes over all ranks (0 = single GPU: use N)
     DevBuf<long long> gid;         // [N] internal order: global reference node id, 0-based (seeds the shadow vectors)
@@ -205,6 +207,9 @@ int mfb_reduce_allreduce(mfb_ctx* ctx, const double* partials, int nb, int k, do
 int mfb_p2p_check(mfb_ctx* ctx);
 bool mfb_is_distributed(mfb_ctx* ctx);
 void mfb_comm_free(mfb_ctx* ctx);
+
+// mfb_meshbuild.cu
+void mfb_meshbuild_free(mfb_ctx* ctx);
 
 // mfb_qp.cu
 int mfb_qp_lookup(mfb_ctx* ctx, const std::string& name, double** p);   // creates the array (zeroed) on first use

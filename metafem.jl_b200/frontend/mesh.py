@@ -114,3 +114,27 @@ def box_tables(size, n, shape="CUBE", groups=("left", "right"), numbering="sorte
         return lambda c: np.abs(c[d] - v) < eps
 
     return second_order_tables(coors, conn, [selector(g) for g in groups], numbering=numbering, seed=seed)
+
+
+def second_order_tables_device(ctx, coors, connections, itg_order=5):
+    """The same tables as ``second_order_tables(..., numbering="sorted")`` built ON THE DEVICE by
+    ``mfb_mesh_build_second_order`` (segments and boundary faces through radix sorts instead of the reference's GPU hash).
+    Returns (controlpoint_IDs, x, bfacet_element_ID, bfacet_element_eindex, bfacet_centroids); the script then selects its
+    boundary groups on the centroids exactly as it does with get_BoundaryMesh (static_Neo_Hookean.jl:19-34)."""
+    import ctypes as C
+    from .. import lib as L
+    connections = np.ascontiguousarray(np.asarray(connections, dtype=np.int32).T)          # [n_el][vpb] == column-major [vpb, n_el]
+    n_el, vpb = connections.shape
+    et = elements.hex20_tables(itg_order) if vpb == 8 else elements.tet10_tables()
+    nv = coors.shape[1]
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    seg, vcp, scp, fv = i32(et.segment_vertices), i32(et.vertex_cp_ids), i32(et.segment_cp_ids), i32(et.face_vertices)
+    x = [np.ascontiguousarray(coors[d], dtype=np.float64) for d in range(3)]
+    N, nbf = C.c_int64(0), C.c_int64(0)
+    ctx.call("mfb_mesh_build_second_order", nv, L.ptr(x[0]), L.ptr(x[1]), L.ptr(x[2]), vpb, n_el, L.ptr(connections), len(seg),
+             L.ptr(seg), L.ptr(vcp), L.ptr(scp), fv.shape[0], fv.shape[1], L.ptr(fv), C.byref(N), C.byref(nbf))
+    cp = np.empty((n_el, et.n_a), np.int32)
+    xo = np.empty((3, N.value))
+    f_el, f_eidx, cen = np.empty(nbf.value, np.int32), np.empty(nbf.value, np.int32), np.empty((nbf.value, 3))
+    ctx.call("mfb_mesh_build_get", L.ptr(cp), L.ptr(xo[0]), L.ptr(xo[1]), L.ptr(xo[2]), L.ptr(f_el), L.ptr(f_eidx), L.ptr(cen))
+    return np.asfortranarray(cp.T), xo, f_el, f_eidx, cen.T

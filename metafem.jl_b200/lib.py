@@ -53,6 +53,10 @@ _SIGS = {
     "mfb_profile_enable": (C.c_int, [_P, C.c_int]),
     "mfb_profile_get": (C.c_int, [_P, _P, _P]),
     "mfb_mesh_set": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "mfb_mesh_build_second_order": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int, C.c_int64, _P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P,
+                                              C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "mfb_mesh_build_get": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "mfb_mesh_build_device_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "mfb_facets_set": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.c_int64, _P, _P]),
     "mfb_boundary_group_set": (C.c_int, [_P, C.c_int, C.c_int64, _P]),
     "mfb_pattern_build": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
