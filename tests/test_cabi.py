@@ -42,7 +42,8 @@ def test_null_context_is_rejected(built_lib):
     assert built_lib.mfb_launch_count(None) == 0
 
 
-@pytest.mark.parametrize("name,na,nq,nqb", [("thermal", 10, 14, 7), ("linear_elasticity", 20, 27, 9), ("neo_hookean", 20, 27, 9)])
+@pytest.mark.parametrize("name,na,nq,nqb", [("thermal", 10, 14, 7), ("linear_elasticity", 20, 27, 9), ("neo_hookean", 20, 27, 9),
+                                            ("thermo_elasticity", 20, 27, 9), ("j2", 20, 27, 9), ("j2_fused", 20, 27, 9)])
 def test_emitted_kernels_compile_for_sm100a(built_lib, name, na, nq, nqb, tmp_path):
     from helpers import spec_for
     src, descs = m.emitter.emit(spec_for(name), na, nq, nqb)
@@ -50,10 +51,25 @@ def test_emitted_kernels_compile_for_sm100a(built_lib, name, na, nq, nqb, tmp_pa
     m.lib.kernel_check(src, cubin)
     blob = open(cubin, "rb").read()
     for d in descs:
-        for k in (d["linear_kernel"], d["nonlinear_kernel"]):
+        for k in (d["linear_kernel"], d["nonlinear_kernel"], d["eval_kernel"]):
             if k:
                 assert k.encode() in blob
     assert all(d["smem_bytes"] < 227 * 1024 for d in descs)
+    # the two-phase J2 form has an argument kernel, the fused one does not and writes the trial state from the residual kernel
+    if name == "j2":
+        assert descs[0]["eval_kernel"] and len(descs[0]["qp_out_names"]) == 6 and len(descs[0]["qp_in_names"]) == 6
+    if name == "j2_fused":
+        assert descs[0]["eval_kernel"] is None and len(descs[0]["qp_in_names"]) == 13 and descs[0]["qp_out_names"][-1] == "j2.count"
+
+
+def test_tangent_tiling_invariants():
+    """The skeleton's static_asserts, checked for a range of element types without compiling."""
+    for n_a in (4, 8, 10, 20, 27):
+        for nv in (1, 2, 3, 4, 6):
+            t = m.emitter._tile(n_a, nv)
+            assert t["NTC"] % 2 == 0 and t["CG"] * t["NTC"] >= n_a and t["LPW"] <= 32
+            assert t["W"] * t["LPW"] >= n_a * nv * t["CG"]
+            assert nv * t["NTC"] <= 60 or t["NTC"] == 2
 
 
 def test_nvrtc_errors_are_reported(built_lib):
