@@ -420,7 +420,7 @@ def main():
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": int(launches), "clocks": clk,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU port is timed beside the single-GPU run only
         try:
             out["cpu_baseline"] = cpu_baseline(args.cpu_n)
         except Exception as e:  # the baseline is a reported number, never a reason to lose the GPU measurement
