@@ -4,9 +4,10 @@
 // src/misc/04_GPU_Utils.jl:86-87,102). Element-block partitioning with *unassembled* interface rows:
 // every rank assembles only its own elements, so a node shared by several ranks carries a partial
 // matrix row / residual entry on each of them. Every vector that comes out of an element loop or an
-// SpMV is completed by mfb_halo_add (pack -> grouped ncclSend/ncclRecv with the neighbours -> sum in
-// ascending rank order, so all copies of a shared entry are bit-identical). Reductions count a node on
-// its owner only and finish with one ncclAllReduce of the whole scalar batch.
+// SpMV is completed by mfb_halo_add (interface entries to the neighbours -- over peer memory, or pack ->
+// grouped ncclSend/ncclRecv -> one merge kernel that sums in ascending rank order, so all copies of a shared
+// entry are bit-identical). Reductions count a node on its owner only and finish with one allreduce of the whole
+// scalar batch (peer-memory mailboxes, or ncclAllReduce).
 // NCCL is bound with dlopen (MFB_NCCL_LIB or libnccl.so.2) so the library loads on machines without it.
 #include <dlfcn.h>
 #include <nccl.h>
@@ -71,23 +72,6 @@ __global__ void k_pack(const double* v, const int* slots, int64_t n, int nv, dou
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n * nv) return;
     buf[t] = v[(size_t)slots[t / nv] * nv + t % nv];
-}
-__global__ void k_zero_slots(double* v, const int* slots, int64_t n, int nv) {
-    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= n * nv) return;
-    v[(size_t)slots[t / nv] * nv + t % nv] = 0.0;
-}
-__global__ void k_add_slots(double* v, const int* slots, int64_t n, int nv, const double* buf) {
-    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= n * nv) return;
-    v[(size_t)slots[t / nv] * nv + t % nv] += buf[t];
-}
-// v = low + v on the union of shared nodes (contributions of lower ranks first)
-__global__ void k_merge_low(double* v, const double* low, const int* slots, int64_t n, int nv) {
-    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= n * nv) return;
-    size_t i = (size_t)slots[t / nv] * nv + t % nv;
-    v[i] = low[i] + v[i];
 }
 // One pass over the union of shared nodes: v[node] = sum over the sharing ranks in ascending rank order, this rank's own
 // value in its place (contributions of lower ranks first, then own, then higher ranks) -- every rank holding the node
@@ -246,7 +230,7 @@ struct Comm {
     DevBuf<int> uni;                       // unique union of slots
     DevBuf<int> uptr, uidx, ulow;          // per union node: receive-buffer positions (ascending neighbour rank), # from lower ranks
     int64_t n_union = 0;
-    DevBuf<double> sendbuf, recvbuf, low;
+    DevBuf<double> sendbuf, recvbuf;
     int buf_nv = 0;
     // peer-memory allreduce
     bool p2p = false;
@@ -352,7 +336,7 @@ void mfb_comm_free(mfb_ctx* ctx) {
     c->p2p_err.release();
     if (c->comm) nccl().CommDestroy(c->comm);
     c->slots.release(); c->uni.release(); c->uptr.release(); c->uidx.release(); c->ulow.release();
-    c->sendbuf.release(); c->recvbuf.release(); c->low.release();
+    c->sendbuf.release(); c->recvbuf.release();
     ctx->owned.release(); ctx->gid.release();
     delete c;
     ctx->comm = nullptr;
