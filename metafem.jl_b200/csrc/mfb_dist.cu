@@ -108,17 +108,7 @@ __global__ void k_owner_internal(const unsigned char* owned_ref, const long long
 // sequence numbers of all peers in its own mailbox and adds the slots in rank order (bit-identical on every rank). The same
 // kernel first folds the per-block partials of the multi-dot kernel, so one launch replaces k_reduce_partials + ncclAllReduce.
 // Two mailboxes are used alternately: a peer can only be one round ahead, so a slot is never overwritten while it is read.
-constexpr int P2P_MAXV = 24;
-constexpr int P2P_MAXR = 16;
-struct P2PSlot {
-    double v[P2P_MAXV];
-    unsigned long long seq;
-    unsigned long long pad[7];
-};
-static_assert(sizeof(P2PSlot) == 256, "mailbox slot is 256 bytes");
-struct P2PPeers {
-    P2PSlot* box[P2P_MAXR];       // mailbox base of every rank: [2 parities][n_ranks slots]
-};
+// (P2PSlot / P2PPeers: mfb_internal.h)
 
 __global__ void __launch_bounds__(256) k_reduce_allreduce_p2p(const double* partials, int nb, int k, double* out, P2PPeers peers,
                                                               int rank, int n_ranks, unsigned long long seq, int* err) {
@@ -424,7 +414,20 @@ extern "C" int mfb_interface_set(mfb_ctx* ctx, int n_neighbors, const int32_t* n
     MFB_CUDA(cudaGetLastError());
     tmp.release(); own.release(); gid.release();
     // ---- peer-memory exchange buffers: every rank publishes its IPC handle and its (neighbour, offset) table ----
-    if (c->p2p && c->comm && c->n_ranks > 1 && n_neighbors <= HALO_MAXNB && n_neighbors <= HALO_FLAGS) {
+    // eligibility is decided COLLECTIVELY (a rank with too many neighbours must not skip the AllGather the others enter)
+    bool halo_ok = c->p2p && c->comm && c->n_ranks > 1;
+    if (halo_ok) {
+        DevBuf<double> elig;
+        MFB_CUDA(elig.alloc(1));
+        const double bad = (n_neighbors <= HALO_MAXNB && n_neighbors <= HALO_FLAGS) ? 0.0 : 1.0;
+        MFB_CUDA(cudaMemcpyAsync(elig.p, &bad, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        MFB_NCCL(nccl().AllReduce(elig.p, elig.p, 1, ncclDouble, ncclSum, c->comm, ctx->stream));
+        double tot = 1.0;
+        MFB_CUDA(cudaMemcpyAsync(&tot, elig.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+        halo_ok = tot == 0.0;
+    }
+    if (halo_ok) {
         NcclApi& api = nccl();
         const int R = c->n_ranks;
         c->hstride = (long long)(HALO_FLAGS * sizeof(unsigned long long) + (size_t)(total > 0 ? total : 1) * HALO_NVMAX * sizeof(double));
@@ -539,6 +542,18 @@ int mfb_reduce_allreduce(mfb_ctx* ctx, const double* partials, int nb, int k, do
     LAUNCH(k_reduce_allreduce_p2p, 1, 256, partials, nb, k, out, c->peers, c->rank, c->n_ranks, c->seq, c->p2p_err.p);
     MFB_CUDA(cudaGetLastError());
     return MFB_OK;
+}
+
+bool mfb_p2p_next(mfb_ctx* ctx, P2PInfo* out) {
+    Comm* c = ctx->comm;
+    if (!c || !c->comm || c->n_ranks == 1 || !c->p2p) return false;
+    c->seq++;
+    out->peers = c->peers;
+    out->rank = c->rank;
+    out->n_ranks = c->n_ranks;
+    out->seq = c->seq;
+    out->err = c->p2p_err.p;
+    return true;
 }
 
 // MFB_ERR_NCCL if a peer-memory allreduce gave up waiting for a peer since the last check (call after a synchronisation)

@@ -141,6 +141,10 @@ struct mfb_ctx {
     std::vector<DevBuf<double>> work;
     DevBuf<double> jac, scal;   // Jacobi vector, device scalars
     DevBuf<double> ksc;         // device-resident Krylov recurrence scalars
+    DevBuf<unsigned> red_counter;        // ticket counter of the fused reductions (last-block detection)
+    DevBuf<unsigned char> kprog;         // fused vector programs of the running solve (device copy)
+    DevBuf<double> Ks;          // Jacobi-scaled copy of K_total for the solve (kept across solves)
+    cudaEvent_t lag_ev[2] = {nullptr, nullptr};   // convergence read-back events (the host lags one outer iteration behind)
     double* h_scal = nullptr;   // pinned host mirror of scal
 
     // ---- staging ----
@@ -198,6 +202,28 @@ int mfb_field_to_internal(mfb_ctx* ctx, const double* ref_field, double* int_fie
 int mfb_export_matrix(mfb_ctx* ctx, const double* Kint, double* Kref_dev);
 int mfb_export_pattern(mfb_ctx* ctx, int* K_I, int* K_J, int* K_J_ptr, int* K_val_ids);  // device ptrs (nullable)
 
+// ---- peer-memory mailboxes of the scalar-batch allreduce (mfb_dist.cu owns them; the reduction epilogues of mfb_krylov.cu
+// publish into / read from them) ----
+constexpr int P2P_MAXV = 24;
+constexpr int P2P_MAXR = 16;
+struct P2PSlot {
+    double v[P2P_MAXV];
+    unsigned long long seq;
+    unsigned long long pad[7];
+};
+static_assert(sizeof(P2PSlot) == 256, "mailbox slot is 256 bytes");
+struct P2PPeers {
+    P2PSlot* box[P2P_MAXR];       // mailbox base of every rank: [2 parities][n_ranks slots]
+};
+struct P2PInfo {
+    P2PPeers peers;
+    int rank = 0, n_ranks = 1;
+    unsigned long long seq = 0;   // sequence number of THIS round (already advanced)
+    int* err = nullptr;
+};
+// true when the peer-memory allreduce is up: fills `out` and advances the round counter (one call per reduction launch)
+bool mfb_p2p_next(mfb_ctx* ctx, P2PInfo* out);
+
 // mfb_dist.cu
 int mfb_node_ids_init(mfb_ctx* ctx, const unsigned char* owned_ref_dev, const long long* gid_ref_dev);
 int mfb_halo_add(mfb_ctx* ctx, double* v, int nv);
@@ -216,4 +242,5 @@ int mfb_qp_lookup(mfb_ctx* ctx, const std::string& name, double** p);   // creat
 
 // mfb_krylov.cu
 int mfb_spmv_internal(mfb_ctx* ctx, const double* K, const double* x, double* y);
+int mfb_spmv_kind(mfb_ctx* ctx);   // 0 = one warp per row (k_spmv_bsr), 1 = multi-row streams (k_spmv_mr)
 int mfb_spmv_t_internal(mfb_ctx* ctx, const double* K, const double* x, double* y);   // y = K' x

@@ -253,14 +253,16 @@ __global__ void k_jacobi_diag(const int* nodeptr, const int* nodecol, const doub
     if (t >= N * nv) return;
     int64_t a = t / nv;
     int v = (int)(t % nv);
-    double j = (owned == nullptr || owned[a]) ? 1.0 : 0.0;   // the default 1.0 must be counted once across ranks
-    if (diag_ok[v]) {
-        j = 0.0;
+    const double one = (owned == nullptr || owned[a]) ? 1.0 : 0.0;   // the default 1.0 must be counted once across ranks
+    double j = one;
+    if (diag_ok[v] && nodeptr[a] < nodeptr[a + 1]) {
         int lo = nodeptr[a], hi = nodeptr[a + 1] - 1;
         while (lo < hi) {
             int mid = (lo + hi) >> 1;
             if (nodecol[mid] < a) lo = mid + 1; else hi = mid;
         }
+        // a partitioned mesh holds the (a,a) block on every rank that holds node a (partial sums: completed by the halo add);
+        // a row WITHOUT a stored diagonal block keeps the 1.0 of Jacobi_By_Diagonal (02_Preconditioner.jl:114-120)
         if (nodecol[lo] == a) j = K[(size_t)lo * nv * nv + v * nv + v];
     }
     jac[t] = j;
@@ -471,6 +473,393 @@ __global__ void k_reduce_partials(const double* partials, int nb, double* out) {
     }
 }
 
+
+// =============================================================================================================
+// Fused reductions. Every group of dot products of a Krylov step is ONE launch: the kernel that produces the vector
+// (SpMV, vector update) also accumulates the dots, each block leaves its partial sums in global memory and the block that
+// finishes last (ticket counter) folds them in a fixed order (bit-reproducible), sums them over the ranks through the
+// peer-memory mailboxes when the mesh is partitioned, and applies the scalar recurrence that consumes them (rho/alpha/beta,
+// tau/sigma/gamma, the convergence test) to the device-resident scalars. The reference does one blocking cuBLAS dot per
+// scalar (03_BiCGstabl.jl:43-93, 04_IDRs.jl:47-93); round 1 of this library needed multidot + fold + one-thread kernel.
+// sc layout (doubles): [0] rho0 [1] alpha [2] omega [3] beta [4] res2 [5] STOP flag [6] iteration counter [7] spare,
+// then the per-method arrays (SC_SIG ... for bicgstabl_GS!, ID_* for idrs!).
+enum { SC_RHO0 = 0, SC_ALPHA = 1, SC_OMEGA = 2, SC_BETA = 3, SC_RES2 = 4, SC_STOP = 5, SC_ITER = 6, SC_SIG = 8, SC_GAMP = 24,
+       SC_GAM = 40, SC_GAMPP = 56, SC_TAU = 72, SC_COUNT = 72 + 16 * 16 };
+enum { OP_NONE = 0, OP_BETA0, OP_BETA, OP_ALPHA, OP_TAU, OP_SIG, OP_FINAL };
+struct ScOp { int op, i, j, off; };
+struct RedCtx {
+    double* sc;          // device scalars (nullptr: no stop flag, no scalar ops)
+    double* red;         // reduced values
+    double* partials;    // [n_dot][gridDim.x]
+    unsigned* counter;   // ticket of the last-block detection (left at 0)
+    double tol, inv_sqrt_n;
+    int maxiter, S;
+    int mode;            // 0 one GPU | 1 peer-memory allreduce in the tail | 2 local fold only (host: ncclAllReduce + k_apply_ops)
+    int rank, n_ranks;
+    unsigned long long seq;
+    int* err;
+    P2PPeers peers;
+};
+
+__device__ __forceinline__ bool stopped(const RedCtx& R) {
+    return R.sc != nullptr && *reinterpret_cast<const volatile double*>(R.sc + SC_STOP) != 0.0;
+}
+
+__device__ void sc_gamma(double* sc, int S) {                                                          // 03_BiCGstabl.jl:72-81
+    double* gam = sc + SC_GAM;
+    const double* gamp = sc + SC_GAMP;
+    const double* tau = sc + SC_TAU;
+    gam[S - 1] = gamp[S - 1];
+    sc[SC_OMEGA] = gam[S - 1];
+    for (int j = S - 2; j >= 0; --j) {
+        double d = 0.0;
+        for (int i = j + 1; i < S; ++i) d += tau[j * S + i] * gam[i];
+        gam[j] = gamp[j] - d;
+    }
+    for (int j = 0; j < S - 1; ++j) {
+        double d = 0.0;
+        for (int i = j + 1; i < S - 1; ++i) d += tau[j * S + i] * gam[i + 1];
+        sc[SC_GAMPP + j] = gam[j + 1] + d;
+    }
+}
+
+// scalar recurrences of bicgstabl_GS! (03_BiCGstabl.jl:43-93), applied by ONE thread to freshly reduced values rd[]
+__device__ void sc_apply(const RedCtx& R, const ScOp& o, const double* red) {
+    double* sc = R.sc;
+    const int S = R.S;
+    const double* rd = red + o.off;
+    switch (o.op) {
+        case OP_BETA0:                                   // rho0 *= -omega (:44), then beta of j = 0
+            sc[SC_RHO0] *= -sc[SC_OMEGA];
+            // fallthrough
+        case OP_BETA: {                                  // (:46-48)
+            const double rho1 = rd[0];
+            sc[SC_BETA] = sc[SC_ALPHA] * rho1 / sc[SC_RHO0];
+            sc[SC_RHO0] = rho1;
+        } break;
+        case OP_ALPHA: sc[SC_ALPHA] = sc[SC_RHO0] / rd[0]; break;                                      // (:54)
+        case OP_TAU: sc[SC_TAU + o.i * S + o.j] = rd[0] / sc[SC_SIG + o.i]; break;                     // (:66)
+        case OP_SIG:                                                                                   // (:69-70, 72-81)
+            sc[SC_SIG + o.j] = rd[0];
+            sc[SC_GAMP + o.j] = rd[1] / rd[0];
+            if (o.j == S - 1) sc_gamma(sc, S);
+            break;
+        case OP_FINAL: {                                 // convergence test of the outer iteration (:92-93), then the next one's opening
+            const double n2 = rd[0];
+            sc[SC_RES2] = n2;
+            const double iter = sc[SC_ITER] + S;
+            sc[SC_ITER] = iter;
+            const double nrm = sqrt(n2) * R.inv_sqrt_n;
+            if (!(nrm > R.tol) || iter >= (double)R.maxiter) {
+                sc[SC_STOP] = 1.0;                       // also on NaN (breakdown)
+            } else {
+                sc[SC_RHO0] *= -sc[SC_OMEGA];
+                const double rho1 = rd[1];
+                sc[SC_BETA] = sc[SC_ALPHA] * rho1 / sc[SC_RHO0];
+                sc[SC_RHO0] = rho1;
+            }
+        } break;
+        default: break;
+    }
+}
+
+__global__ void k_apply_ops(RedCtx R, ScOp o0, ScOp o1) {
+    if (stopped(R)) return;
+    if (o0.op != OP_NONE) sc_apply(R, o0, R.red);
+    if (o1.op != OP_NONE) sc_apply(R, o1, R.red);
+}
+
+// sum of v over the 256 threads of the block, valid in thread 0 (sh: 8 doubles)
+__device__ __forceinline__ double block_sum256(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double w = 0.0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w += sh[i];
+    }
+    return w;
+}
+
+// Tail of every reducing kernel (256 threads per block; thread 0 of each block has already stored the block's partial sums at
+// partials[d * gridDim.x + blockIdx.x]). The last block to arrive folds, exchanges with the other ranks, applies the scalar ops.
+__device__ __noinline__ void reduce_tail(const RedCtx& R, int nd, const ScOp& o0, const ScOp& o1) {
+    __shared__ int s_last;
+    __shared__ double s_w[8];
+    __shared__ double s_loc[P2P_MAXV];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        __threadfence();
+        const unsigned t = atomicAdd(R.counter, 1u);
+        s_last = (t == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int nb = gridDim.x;
+    for (int d = 0; d < nd; ++d) {
+        double v = 0.0;
+        for (int b = tid; b < nb; b += 256) v += __ldcg(R.partials + (size_t)d * nb + b);
+        const double w = block_sum256(v, s_w);
+        if (tid == 0) s_loc[d] = w;
+    }
+    __syncthreads();
+    if (R.mode == 1) {
+        const int par = (int)(R.seq & 1ull);
+        if (tid < R.n_ranks) {                              // publish to every mailbox (including the own one)
+            P2PSlot* dst = R.peers.box[tid] + par * R.n_ranks + R.rank;
+            for (int d = 0; d < nd; ++d) ((volatile double*)dst->v)[d] = s_loc[d];
+            __threadfence_system();
+            *((volatile unsigned long long*)&dst->seq) = R.seq;
+        }
+        if (tid < R.n_ranks) {                              // wait for every rank's contribution of this round
+            const P2PSlot* src = R.peers.box[R.rank] + par * R.n_ranks + tid;
+            long long spins = 0;
+            while (*((volatile const unsigned long long*)&src->seq) < R.seq) {
+                if (++spins > 40000000ll) { atomicExch(R.err, 1); break; }    // ~10 s: a peer died; do not hang the GPU
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+        double sum = 0.0;
+        if (tid < nd) {
+            const P2PSlot* src = R.peers.box[R.rank] + par * R.n_ranks;
+            for (int r = 0; r < R.n_ranks; ++r) sum += ((volatile const double*)src[r].v)[tid];   // rank order: same bits everywhere
+        }
+        __syncthreads();
+        if (tid < nd) s_loc[tid] = sum;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        for (int d = 0; d < nd; ++d) R.red[d] = s_loc[d];
+        if (R.mode != 2 && R.sc != nullptr) {
+            if (o0.op != OP_NONE) sc_apply(R, o0, s_loc);
+            if (o1.op != OP_NONE) sc_apply(R, o1, s_loc);
+        }
+        *R.counter = 0u;
+    }
+}
+
+// ---- fused vector program: a short list of updates y_u = ay_u * y_u + sum_t c_t x_t (coefficients = host constant times an
+// optional device-resident scalar), executed in order for every index, followed by dot products whose operands are vectors
+// or the result of the LAST update (still in registers), the cross-block fold and the scalar ops. The programs of one outer
+// iteration are built once per solve and live in device memory (8-byte kernel argument instead of a 2-3 kB struct).
+constexpr int FU_MAXU = 18;   // updates per program (bicgstabl needs s + 2)
+constexpr int FU_MAXT = 56;   // terms per program
+constexpr int FU_MAXD = 24;   // dots per program
+struct FusedTerm { const double* x; const double* cp; double c; };
+struct FusedUpd { double* y; const double* ayp; double ay; int t0, nt; };
+struct Fused {
+    int n_upd, n_term, n_dot, pad;
+    FusedUpd u[FU_MAXU];
+    FusedTerm t[FU_MAXT];
+    const double* dx[FU_MAXD];    // dot d = sum_i X_i * Y_i, X = dx[d] (nullptr: result of the last update), Y likewise
+    const double* dy[FU_MAXD];
+    ScOp ops[2];
+};
+static_assert(sizeof(Fused) % 8 == 0, "Fused is copied to shared memory in 8-byte words");
+
+__device__ __forceinline__ double2 ld2(const double* p, int64_t pair, int64_t n) {
+    if (2 * pair + 1 < n) return *reinterpret_cast<const double2*>(p + 2 * pair);
+    return make_double2(p[2 * pair], 0.0);
+}
+__device__ __forceinline__ void st2(double* p, int64_t pair, int64_t n, double2 v) {
+    if (2 * pair + 1 < n) *reinterpret_cast<double2*>(p + 2 * pair) = v;
+    else p[2 * pair] = v.x;
+}
+
+template <int ND>
+__global__ void __launch_bounds__(256) k_fused(const Fused* __restrict__ Fg, const RedCtx R, int64_t n, const unsigned char* owned,
+                                               int nv) {
+    if (stopped(R)) return;
+    __shared__ Fused F;
+    __shared__ double s_c[FU_MAXT], s_ay[FU_MAXU], s_w[8];
+    const int tid = threadIdx.x;
+    {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(Fg);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&F);
+        for (int i = tid; i < (int)(sizeof(Fused) / 8); i += 256) dst[i] = src[i];
+    }
+    __syncthreads();
+    if (tid < F.n_term) s_c[tid] = F.t[tid].cp ? F.t[tid].c * __ldcg(F.t[tid].cp) : F.t[tid].c;
+    if (tid < F.n_upd) s_ay[tid] = F.u[tid].ayp ? F.u[tid].ay * __ldcg(F.u[tid].ayp) : F.u[tid].ay;
+    __syncthreads();
+    double acc[ND > 0 ? ND : 1];
+#pragma unroll
+    for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
+    const int64_t np = (n + 1) >> 1;                      // element pairs: 128-bit loads and stores
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t p0 = blockIdx.x * (int64_t)256 + tid; p0 < np; p0 += 2 * stride) {
+        const int64_t p1 = p0 + stride;
+        const bool ok1 = p1 < np;
+        double2 r0 = make_double2(0.0, 0.0), r1 = make_double2(0.0, 0.0);
+        for (int u = 0; u < F.n_upd; ++u) {
+            double* yp = F.u[u].y;
+            const double ay = s_ay[u];
+            double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
+            if (ay != 0.0) {
+                a0 = ld2(yp, p0, n);
+                if (ok1) a1 = ld2(yp, p1, n);
+                a0.x *= ay; a0.y *= ay; a1.x *= ay; a1.y *= ay;
+            }
+            const int t1 = F.u[u].t0 + F.u[u].nt;
+            for (int t = F.u[u].t0; t < t1; ++t) {
+                const double c = s_c[t];
+                const double* xp = F.t[t].x;
+                const double2 x0 = ld2(xp, p0, n);
+                const double2 x1 = ok1 ? ld2(xp, p1, n) : make_double2(0.0, 0.0);
+                a0.x += c * x0.x; a0.y += c * x0.y; a1.x += c * x1.x; a1.y += c * x1.y;
+            }
+            st2(yp, p0, n, a0);
+            if (ok1) st2(yp, p1, n, a1);
+            r0 = a0; r1 = a1;
+        }
+        if constexpr (ND > 0) {
+            double2 w0 = make_double2(1.0, 2 * p0 + 1 < n ? 1.0 : 0.0), w1 = make_double2(ok1 ? 1.0 : 0.0, (ok1 && 2 * p1 + 1 < n) ? 1.0 : 0.0);
+            if (owned != nullptr) {                         // count every node once (on its owner)
+                w0.x = owned[(2 * p0) / nv] ? 1.0 : 0.0;
+                if (w0.y != 0.0) w0.y = owned[(2 * p0 + 1) / nv] ? 1.0 : 0.0;
+                if (w1.x != 0.0) w1.x = owned[(2 * p1) / nv] ? 1.0 : 0.0;
+                if (w1.y != 0.0) w1.y = owned[(2 * p1 + 1) / nv] ? 1.0 : 0.0;
+            }
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+                if (d < F.n_dot) {
+                    const double* xp = F.dx[d];
+                    const double* yp = F.dy[d];
+                    const double2 x0 = xp ? ld2(xp, p0, n) : r0, x1 = xp ? (ok1 ? ld2(xp, p1, n) : make_double2(0.0, 0.0)) : r1;
+                    const double2 y0 = yp ? ld2(yp, p0, n) : r0, y1 = yp ? (ok1 ? ld2(yp, p1, n) : make_double2(0.0, 0.0)) : r1;
+                    acc[d] += (w0.x * (x0.x * y0.x) + w0.y * (x0.y * y0.y)) + (w1.x * (x1.x * y1.x) + w1.y * (x1.y * y1.y));
+                }
+        }
+    }
+    if constexpr (ND > 0) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+            if (d < F.n_dot) {
+                const double w = block_sum256(acc[d], s_w);
+                if (tid == 0) R.partials[(size_t)d * gridDim.x + blockIdx.x] = w;
+            }
+        reduce_tail(R, F.n_dot, F.ops[0], F.ops[1]);
+    }
+}
+
+// ---- SpMV, multi-row streams: one warp walks the CONCATENATED value stream of RW consecutive block rows (they are contiguous
+// in memory) with the same software pipeline as k_spmv_bsr, so the dependent chain nodeptr -> (values, column ids) -> x[col]
+// is restarted once per RW rows (~ 8 x 4 batches) instead of once per row (~ 4 batches: about one exposed DRAM latency in
+// five). Row boundaries inside a batch are resolved with predicated adds on the (rare) slow path; a batch that lies inside one
+// row takes the FMA fast path. With DOT the kernel also accumulates sum_rows w[row] . y[row] (the dot product the Krylov
+// method takes of the fresh product: r_shadow' A u) and finishes it in its tail: no second pass over y, no extra launch.
+template <int NV, int UNR, int RW, bool DOT, int MINB = 0>
+__global__ void __launch_bounds__(256, MINB) k_spmv_mr(const int* __restrict__ nodeptr, const int* __restrict__ nodecol,
+                                                 const double* __restrict__ K, const double* __restrict__ x,
+                                                 double* __restrict__ y, int64_t N, const double* __restrict__ wdot,
+                                                 const RedCtx R, const ScOp op0) {
+    if (stopped(R)) return;
+    constexpr int B = NV * NV, EPW = 32 / B, ACTIVE = EPW * B, W = UNR * EPW;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int le = lane / B, ik = lane - le * B, i = ik / NV, k = ik - i * NV;
+    const bool on = lane < ACTIVE;
+    const double* xk = x + k;
+    double dacc = 0.0;
+    const int64_t row0 = (blockIdx.x * (int64_t)8 + warp) * RW;
+    if (row0 < N) {
+        const int nr = (int)min((int64_t)RW, N - row0);
+        const int myp = (lane <= nr) ? __ldg(nodeptr + row0 + lane) : 0;     // lane l holds nodeptr[row0 + l]
+        const int s = __shfl_sync(FULL, myp, 0);
+        const int degw = __shfl_sync(FULL, myp, nr) - s;                     // length of the whole stream (warp-uniform)
+        const int deg = on ? degw : 0;
+        int cr = 0, lo = 0, hi = __shfl_sync(FULL, myp, 1) - s;              // current row and its entry range within the stream
+        const double* Kp = K + (size_t)s * B + lane;
+        const int* Cp = nodecol + s + le;
+        double a[UNR], v[UNR];
+        int c[UNR];
+        int e = le, base = 0;
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            a[u] = 0.0;
+            const bool ok = e + u * EPW < deg;
+            v[u] = ok ? __ldcs(Kp + u * ACTIVE) : 0.0;
+            c[u] = ok ? __ldg(Cp + u * EPW) : 0;
+        }
+        for (;;) {
+            double vn[UNR];
+            int cn[UNR];
+            Kp += UNR * ACTIVE;
+            Cp += UNR * EPW;
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {                                  // streams of the NEXT batch first ...
+                const bool ok = e + W + u * EPW < deg;
+                vn[u] = ok ? __ldcs(Kp + u * ACTIVE) : 0.0;
+                cn[u] = ok ? __ldg(Cp + u * EPW) : 0;
+            }
+            double xg[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) xg[u] = __ldg(xk + (size_t)c[u] * NV);   // ... then the dependent gathers of this one
+            const int bend = base + W;
+            if (bend < hi) {                                                  // the whole batch lies inside row cr
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) a[u] = fma(v[u], xg[u], a[u]);
+            } else {                                                          // the batch reaches the end of row cr
+                double p[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) p[u] = v[u] * xg[u];
+                for (;;) {
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) {
+                        const int eu = e + u * EPW;
+                        if (eu >= lo && eu < hi) a[u] += p[u];
+                    }
+                    double acc = 0.0;
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) { acc += a[u]; a[u] = 0.0; }
+                    double t = acc;
+#pragma unroll
+                    for (int d = 1; d < NV; ++d) t += __shfl_down_sync(FULL, acc, d);           // sum over k
+                    double r = t;
+                    if constexpr ((B & (B - 1)) == 0) {
+#pragma unroll
+                        for (int o = 16; o >= B; o >>= 1) r += __shfl_xor_sync(FULL, r, o);
+                    } else {
+#pragma unroll
+                        for (int d = 1; d < EPW; ++d) r += __shfl_down_sync(FULL, t, d * B);    // sum over the EPW entries
+                    }
+                    if (le == 0 && k == 0 && on) {
+                        const size_t at = (size_t)(row0 + cr) * NV + i;
+                        y[at] = r;
+                        if constexpr (DOT) dacc += r * __ldg(wdot + at);
+                    }
+                    ++cr;
+                    lo = hi;
+                    if (cr >= nr) break;
+                    hi = __shfl_sync(FULL, myp, cr + 1) - s;
+                    if (bend < hi) {                                          // row cr goes on in later batches: take its share of this one
+#pragma unroll
+                        for (int u = 0; u < UNR; ++u)
+                            if (e + u * EPW >= lo) a[u] += p[u];
+                        break;
+                    }
+                }
+                if (cr >= nr) break;
+            }
+            base = bend;
+            e += W;
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) { v[u] = vn[u]; c[u] = cn[u]; }
+        }
+    }
+    if constexpr (DOT) {
+        __shared__ double s_w[8];
+        const double w = block_sum256(dacc, s_w);
+        if (threadIdx.x == 0) R.partials[blockIdx.x] = w;
+        reduce_tail(R, 1, op0, ScOp{OP_NONE, 0, 0, 0});
+    }
+}
+
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
     z += 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -490,12 +879,10 @@ __global__ void k_rand(double* p, int64_t n, unsigned long long seed, unsigned l
 // ---- device-resident scalar recurrences of bicgstabl_GS! (03_BiCGstabl.jl:43-93): one thread, enqueued between the
 // vector kernels so that an outer iteration needs ONE host synchronisation (the convergence test) instead of 19.
 // sc layout: [0] rho0 [1] alpha [2] omega [3] beta [4] res2 [8 + j] sig [24 + j] gamp [40 + j] gam [56 + j] gampp [72 + i*S + j] tau
-enum { SC_RHO0 = 0, SC_ALPHA = 1, SC_OMEGA = 2, SC_BETA = 3, SC_RES2 = 4, SC_SIG = 8, SC_GAMP = 24, SC_GAM = 40, SC_GAMPP = 56,
-       SC_TAU = 72, SC_COUNT = 72 + 16 * 16 };
 __global__ void k_sc_init(double* sc) {
     for (int i = threadIdx.x; i < SC_COUNT; i += blockDim.x) sc[i] = 0.0;
     __syncthreads();
-    if (threadIdx.x == 0) { sc[SC_RHO0] = 1.0; sc[SC_OMEGA] = 1.0; sc[SC_ALPHA] = 0.0; }
+    if (threadIdx.x == 0) { sc[SC_RHO0] = 1.0; sc[SC_OMEGA] = 1.0; sc[SC_ALPHA] = 0.0; sc[SC_ITER] = 1.0; }
 }
 __global__ void k_sc_outer_begin(double* sc) { sc[SC_RHO0] *= -sc[SC_OMEGA]; }                        // rho0 *= -omega (:44)
 __global__ void k_sc_beta(double* sc, const double* red) {                                            // (:46-48)
@@ -600,11 +987,68 @@ int mfb_spmv_t_internal(mfb_ctx* ctx, const double* K, const double* x, double* 
     return MFB_OK;
 }
 
-int mfb_spmv_internal(mfb_ctx* ctx, const double* K, const double* x, double* y) {
+int mfb_spmv_kind(mfb_ctx* ctx) {
+    (void)ctx;
+    static int kind = -1;
+    if (kind < 0) {
+        const char* e = getenv("MFB_SPMV");
+        kind = (e && (e[0] == 'r' || e[0] == '0')) ? 0 : 1;      // MFB_SPMV=row: one warp per row (round-1 kernel); default: multi-row streams
+    }
+    return kind;
+}
+
+namespace {
+int spmv_rw() {
+    static int rw = -1;
+    if (rw < 0) {
+        const char* e = getenv("MFB_SPMV_RW");
+        rw = e ? atoi(e) : 8;
+        if (rw != 4 && rw != 16) rw = 8;
+    }
+    return rw;
+}
+RedCtx null_redctx() {
+    RedCtx R;
+    memset(&R, 0, sizeof(R));
+    return R;
+}
+template <int NV, int RW>
+void launch_spmv_mr(mfb_ctx* ctx, const double* K, const double* x, double* y, const double* w, const RedCtx& R, const ScOp& op) {
     const int64_t N = ctx->N;
+    const unsigned grid = (unsigned)((N + 8 * RW - 1) / (8 * RW));
+    // the register cap keeps the fused-dot variant at the occupancy of the plain one (its fold / scalar-op tail, executed by one
+    // block, may spill instead)
+    constexpr int MINB = NV <= 3 ? 4 : (NV == 4 ? 3 : 2);
+    if (w) k_spmv_mr<NV, SpmvUnroll<NV>::value, RW, true, MINB><<<grid, 256, 0, ctx->stream>>>(ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N, w, R, op);
+    else k_spmv_mr<NV, SpmvUnroll<NV>::value, RW, false, MINB><<<grid, 256, 0, ctx->stream>>>(ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N, w, R, op);
+    ctx->launches++;
+}
+}  // namespace
+
+// y = K x (block rows of this rank). w != nullptr (multi-row kernel only): also red[0] = sum_rows w . y, folded and followed by
+// the scalar op in the kernel's tail; R.sc != nullptr: the launch is skipped on the device once the solver's stop flag is up.
+static int spmv_launch(mfb_ctx* ctx, const double* K, const double* x, double* y, const double* w, const RedCtx& R, const ScOp& op) {
+    const int64_t N = ctx->N;
+    ProfScope ps(ctx, MFB_T_SPMV);
+    if (mfb_spmv_kind(ctx) == 1 && ctx->n_var <= 5) {
+        const int rw = spmv_rw();
+        switch (ctx->n_var) {
+            case 1: launch_spmv_mr<1, 8>(ctx, K, x, y, w, R, op); break;
+            case 2: launch_spmv_mr<2, 8>(ctx, K, x, y, w, R, op); break;
+            case 3:
+                if (rw == 4) launch_spmv_mr<3, 4>(ctx, K, x, y, w, R, op);
+                else if (rw == 16) launch_spmv_mr<3, 16>(ctx, K, x, y, w, R, op);
+                else launch_spmv_mr<3, 8>(ctx, K, x, y, w, R, op);
+                break;
+            case 4: launch_spmv_mr<4, 8>(ctx, K, x, y, w, R, op); break;
+            case 5: launch_spmv_mr<5, 8>(ctx, K, x, y, w, R, op); break;
+        }
+        MFB_CUDA(cudaGetLastError());
+        return MFB_OK;
+    }
+    MFB_REQUIRE(w == nullptr, MFB_ERR_STATE, "fused SpMV dot needs the multi-row kernel");
     unsigned grid = (unsigned)((N + SPMV_ROWS - 1) / SPMV_ROWS);
     const unsigned gridf = (unsigned)((N * 32 + 255) / 256);
-    ProfScope ps(ctx, MFB_T_SPMV);
     switch (ctx->n_var) {
         case 1: LAUNCH(k_spmv_bsr<1>, grid, 256, ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N); break;
         case 2: LAUNCH(k_spmv_bsr<2>, grid, 256, ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N); break;
@@ -616,6 +1060,10 @@ int mfb_spmv_internal(mfb_ctx* ctx, const double* K, const double* x, double* y)
     }
     MFB_CUDA(cudaGetLastError());
     return MFB_OK;
+}
+
+int mfb_spmv_internal(mfb_ctx* ctx, const double* K, const double* x, double* y) {
+    return spmv_launch(ctx, K, x, y, nullptr, null_redctx(), ScOp{OP_NONE, 0, 0, 0});
 }
 
 namespace {
@@ -728,6 +1176,109 @@ struct Solver {
     }
     double n_global = 0.0;   // global number of DOFs (sum of owned nodes over ranks)
     double nn(double norm2) const { return std::sqrt(norm2) / std::sqrt(n_global > 0 ? n_global : (double)n); }  // normalized_norm
+
+    // ---- fused reductions (device-resident scalars, no host synchronisation) ----
+    double f_tol = 0.0;
+    int f_maxiter = 0, f_S = 0;
+    std::vector<Fused> progs;          // host copies of the fused programs of this solve
+    // reduction context of the NEXT reducing launch (advances the mailbox round on a partitioned mesh)
+    RedCtx redctx(bool with_sc = true) {
+        RedCtx R;
+        memset(&R, 0, sizeof(R));
+        R.sc = with_sc ? ctx->ksc.p : nullptr;
+        R.red = ctx->scal.p;
+        R.partials = ctx->scal.p + 64;
+        R.counter = ctx->red_counter.p;
+        R.tol = f_tol;
+        R.inv_sqrt_n = 1.0 / std::sqrt(n_global > 0 ? n_global : (double)n);
+        R.maxiter = f_maxiter;
+        R.S = f_S;
+        R.mode = 0;
+        if (mfb_is_distributed(ctx)) {
+            P2PInfo I;
+            if (mfb_p2p_next(ctx, &I)) {
+                R.mode = 1; R.rank = I.rank; R.n_ranks = I.n_ranks; R.seq = I.seq; R.err = I.err; R.peers = I.peers;
+            } else {
+                R.mode = 2;
+            }
+        }
+        return R;
+    }
+    RedCtx stopctx() {                   // for launches that only honour the stop flag
+        RedCtx R;
+        memset(&R, 0, sizeof(R));
+        R.sc = ctx->ksc.p;
+        return R;
+    }
+    // NCCL fallback of a reducing launch: sum red[0..nd) over the ranks, then the scalar ops in a one-thread kernel
+    int after_reduce(const RedCtx& R, int nd, const ScOp& o0, const ScOp& o1) {
+        if (R.mode != 2) return MFB_OK;
+        MFB_TRY(mfb_allreduce_sum(ctx, ctx->scal.p, nd));
+        if (R.sc && (o0.op != OP_NONE || o1.op != OP_NONE)) LAUNCH(k_apply_ops, 1, 1, R, o0, o1);
+        return MFB_OK;
+    }
+    int upload_programs() {
+        MFB_CUDA(ctx->kprog.alloc(progs.size() * sizeof(Fused)));
+        MFB_CUDA(cudaMemcpyAsync(ctx->kprog.p, progs.data(), progs.size() * sizeof(Fused), cudaMemcpyHostToDevice, ctx->stream));
+        MFB_CUDA(cudaStreamSynchronize(ctx->stream));     // progs may be rebuilt by the next pass
+        return MFB_OK;
+    }
+    int run(int idx) {
+        const Fused& F = progs[idx];
+        const Fused* dev = reinterpret_cast<const Fused*>(ctx->kprog.p) + idx;
+        const int nd = F.n_dot;
+        if (nd == 0) {
+            LAUNCH((k_fused<0>), RED_BLOCKS, TPB, dev, stopctx(), n, (const unsigned char*)nullptr, ctx->n_var);
+            return MFB_OK;
+        }
+        ProfScope ps(ctx, MFB_T_REDUCE);
+        const RedCtx R = redctx();
+        if (nd <= 2) LAUNCH((k_fused<2>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
+        else if (nd <= 4) LAUNCH((k_fused<4>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
+        else if (nd <= 8) LAUNCH((k_fused<8>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
+        else LAUNCH((k_fused<FU_MAXD>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
+        return after_reduce(R, nd, F.ops[0], F.ops[1]);
+    }
+    // y = A x with the dot w'y (+ scalar op) fused into the SpMV tail when the product needs no completion by other ranks
+    // and no left preconditioner; otherwise SpMV (+ interface exchange, + Pl) followed by the program `dot_prog`
+    bool can_fuse_spmv_dot() const { return mfb_spmv_kind(ctx) == 1 && ctx->n_var <= 5 && !pl && !mfb_is_distributed(ctx); }
+    int mul_dot(double* y, const double* x, const double* w, const ScOp& op, int dot_prog) {
+        spmv++;
+        if (w && can_fuse_spmv_dot()) {
+            const RedCtx R = redctx();
+            return spmv_launch(ctx, A, x, y, w, R, op);
+        }
+        MFB_TRY(spmv_launch(ctx, A, x, y, nullptr, stopctx(), ScOp{OP_NONE, 0, 0, 0}));
+        MFB_TRY(mfb_halo_add(ctx, y, ctx->n_var));
+        MFB_TRY(Pl(y));
+        if (w) MFB_TRY(run(dot_prog));
+        return MFB_OK;
+    }
+};
+
+// builder of one fused program
+struct FB {
+    Fused F;
+    FB() { memset(&F, 0, sizeof(F)); }
+    FB& upd(double* y, double ay, const double* ayp = nullptr) {
+        FusedUpd& U = F.u[F.n_upd++];
+        U.y = y; U.ay = ay; U.ayp = ayp; U.t0 = F.n_term; U.nt = 0;
+        return *this;
+    }
+    FB& term(double c, const double* cp, const double* x) {
+        FusedTerm& T = F.t[F.n_term++];
+        T.c = c; T.cp = cp; T.x = x;
+        F.u[F.n_upd - 1].nt++;
+        return *this;
+    }
+    FB& dot(const double* x, const double* y) {      // nullptr operand: the result of the last update
+        F.dx[F.n_dot] = x; F.dy[F.n_dot] = y; F.n_dot++;
+        return *this;
+    }
+    FB& op(int which, int code, int i, int j, int off) {
+        F.ops[which] = ScOp{code, i, j, off};
+        return *this;
+    }
 };
 
 // r = Pl(b - A x) (the opening lines of every solver) or, with left == false, the plain b - A x of iterative_Solve!;
@@ -855,8 +1406,8 @@ int idrs(Solver& S, double* x, const double* b, double* r, double tol, int maxit
 // Same operations in the same order as the reference; the scalars (rho, alpha, beta, tau, sigma, gamma...) live on the
 // device and are updated by one-thread kernels between the vector kernels, so the stream never drains inside an outer
 // iteration: one host synchronisation per 2 s SpMVs (the convergence test) instead of one per dot product.
-int bicgstabl_gs(Solver& S, double* x, const double* b, double* r, double tol, int maxiter, int s, uint64_t seed,
-                 int pass, std::vector<double*>& W, int* iters) {
+int bicgstabl_gs_legacy(Solver& S, double* x, const double* b, double* r, double tol, int maxiter, int s, uint64_t seed,
+                        int pass, std::vector<double*>& W, int* iters) {
     mfb_ctx* ctx = S.ctx;
     const int64_t n = S.n;
     double res;
@@ -936,10 +1487,120 @@ int bicgstabl_gs(Solver& S, double* x, const double* b, double* r, double tol, i
     }
 }
 
+// bicgstabl_GS!  (03_BiCGstabl.jl:18-96), fused form. Same operations in the same order as the reference, but
+//  * every dot product rides in the kernel that produces its operand: r_shadow'(A u) in the SpMV tail, the Gram-Schmidt
+//    coefficients of the MR part in the update that precedes them, ||r||^2 and the next rho in the closing update;
+//  * the scalar recurrences run in the tail of those kernels (reduce_tail / sc_apply): no one-thread kernels;
+//  * the convergence test sets a device-side stop flag that every later launch honours, and the host reads it back one outer
+//    iteration late: the stream never drains (round 1: one synchronisation per outer iteration, 82 launches per 2 s SpMVs;
+//    now 3 s + 12 for s = 4, i.e. 3 per SpMV on one GPU).
+int bicgstabl_gs(Solver& S, double* x, const double* b, double* r, double tol, int maxiter, int s, uint64_t seed,
+                 int pass, std::vector<double*>& W, int* iters) {
+    mfb_ctx* ctx = S.ctx;
+    const int64_t n = S.n;
+    double res;
+    MFB_TRY(true_residual(S, r, b, x, &res));
+    if (res <= tol) { *iters = 0; return MFB_OK; }
+    if (s > 16) { ctx->err = "bicgstabl_GS: s > 16"; return MFB_ERR_ARG; }
+    std::vector<double*> R(s + 1), U(s + 1);
+    R[0] = r;
+    for (int i = 1; i <= s; ++i) R[i] = W[i - 1];
+    for (int i = 0; i <= s; ++i) U[i] = W[s + i];
+    double* r_shadow = W[2 * s + 1];
+    LAUNCH(k_rand, RED_BLOCKS, TPB, r_shadow, n, (unsigned long long)seed, (unsigned long long)(pass * 64 + 63), ctx->gid.p, ctx->n_var);
+    for (int i = 1; i <= s; ++i) MFB_CUDA(cudaMemsetAsync(R[i], 0, n * sizeof(double), ctx->stream));
+    for (int i = 0; i <= s; ++i) MFB_CUDA(cudaMemsetAsync(U[i], 0, n * sizeof(double), ctx->stream));
+    MFB_CUDA(ctx->ksc.alloc(SC_COUNT));
+    double* sc = ctx->ksc.p;
+    LAUNCH(k_sc_init, 1, 128, sc);
+    S.f_tol = tol; S.f_maxiter = maxiter; S.f_S = s;
+    const bool fuse = S.can_fuse_spmv_dot();
+    // ---- programs of one outer iteration ----
+    S.progs.clear();
+    auto add = [&](const FB& fb) { S.progs.push_back(fb.F); return (int)S.progs.size() - 1; };
+    const int p_rho0 = add(FB().dot(r_shadow, R[0]).op(0, OP_BETA0, 0, 0, 0));          // opening of the first outer iteration
+    std::vector<int> pa(s), pd(s), pdotU(s, -1), pdotR(s, -1);
+    for (int j = 0; j < s; ++j) {
+        FB a;                                                                             // U[i] = R[i] - beta U[i], i <= j  (:49-51)
+        for (int i = 0; i <= j; ++i) a.upd(U[i], -1.0, sc + SC_BETA).term(1.0, nullptr, R[i]);
+        pa[j] = add(a);
+        FB d;                                                                             // R[i] -= alpha U[i+1]; x += alpha U[0]  (:55-58)
+        for (int i = 0; i <= j; ++i) d.upd(R[i], 1.0).term(-1.0, sc + SC_ALPHA, U[i + 1]);
+        d.upd(x, 1.0).term(1.0, sc + SC_ALPHA, U[0]);
+        pd[j] = add(d);
+        if (!fuse) {
+            pdotU[j] = add(FB().dot(r_shadow, U[j + 1]).op(0, OP_ALPHA, 0, 0, 0));
+            if (j < s - 1) pdotR[j] = add(FB().dot(r_shadow, R[j + 1]).op(0, OP_BETA, 0, 0, 0));
+        }
+    }
+    // MR part by modified Gram-Schmidt (:62-71): row j needs tau_ij = <R[i+1], R[j+1]> / sig_i one after the other
+    std::vector<int> pmr;
+    {
+        FB m0;                                                                            // j = 0: sig_0, gamp_0 (+ tau_01 for the next row)
+        m0.dot(R[1], R[1]).dot(R[0], R[1]).op(0, OP_SIG, 0, 0, 0);
+        if (s > 1) m0.dot(R[1], R[2]).op(1, OP_TAU, 0, 1, 2);
+        pmr.push_back(add(m0));
+        for (int j = 1; j < s; ++j)
+            for (int i = 0; i < j; ++i) {
+                FB m;
+                m.upd(R[j + 1], 1.0).term(-1.0, sc + SC_TAU + i * s + j, R[i + 1]);       // R[j+1] -= tau_ij R[i+1]
+                if (i < j - 1) {
+                    m.dot(R[i + 2], nullptr).op(0, OP_TAU, i + 1, j, 0);
+                } else {
+                    m.dot(nullptr, nullptr).dot(R[0], nullptr).op(0, OP_SIG, 0, j, 0);    // sig_j, gamp_j (and the gammas after the last row)
+                    if (j < s - 1) m.dot(R[1], R[j + 2]).op(1, OP_TAU, 0, j + 1, 2);
+                }
+                pmr.push_back(add(m));
+            }
+    }
+    FB fin;                                                                               // (:83-91), then ||r||^2 and the next rho
+    fin.upd(x, 1.0).term(1.0, sc + SC_GAM, R[0]);
+    for (int j = 0; j < s - 1; ++j) fin.term(1.0, sc + SC_GAMPP + j, R[j + 1]);
+    fin.upd(U[0], 1.0).term(-1.0, sc + SC_GAM + s - 1, U[s]);
+    for (int j = 0; j < s - 1; ++j) fin.term(-1.0, sc + SC_GAM + j, U[j + 1]);
+    fin.upd(R[0], 1.0).term(-1.0, sc + SC_GAMP + s - 1, R[s]);
+    for (int j = 0; j < s - 1; ++j) fin.term(-1.0, sc + SC_GAMP + j, R[j + 1]);
+    fin.dot(nullptr, nullptr).dot(r_shadow, nullptr).op(0, OP_FINAL, 0, 0, 0);
+    const int p_fin = add(fin);
+    MFB_TRY(S.upload_programs());
+    // ---- run: the host enqueues outer iteration k + 1 before it knows the outcome of k ----
+    for (int q = 0; q < 2; ++q)
+        if (!ctx->lag_ev[q]) MFB_CUDA(cudaEventCreateWithFlags(&ctx->lag_ev[q], cudaEventDisableTiming));
+    double* hslot = ctx->h_scal + 32;                 // two read-back slots of 8 doubles: sc[0..8)
+    MFB_TRY(S.run(p_rho0));
+    const ScOp none{OP_NONE, 0, 0, 0};
+    for (int k = 0;; ++k) {
+        for (int j = 0; j < s; ++j) {
+            MFB_TRY(S.run(pa[j]));
+            MFB_TRY(S.mul_dot(U[j + 1], U[j], r_shadow, ScOp{OP_ALPHA, 0, 0, 0}, pdotU[j]));
+            MFB_TRY(S.run(pd[j]));
+            if (j < s - 1) MFB_TRY(S.mul_dot(R[j + 1], R[j], r_shadow, ScOp{OP_BETA, 0, 0, 0}, pdotR[j]));
+            else MFB_TRY(S.mul_dot(R[j + 1], R[j], nullptr, none, -1));
+        }
+        for (int pm : pmr) MFB_TRY(S.run(pm));
+        MFB_TRY(S.run(p_fin));
+        MFB_CUDA(cudaMemcpyAsync(hslot + 8 * (k & 1), sc, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        MFB_CUDA(cudaEventRecord(ctx->lag_ev[k & 1], ctx->stream));
+        if (k >= 1) {
+            MFB_CUDA(cudaEventSynchronize(ctx->lag_ev[(k - 1) & 1]));
+            if (hslot[8 * ((k - 1) & 1) + SC_STOP] != 0.0) break;
+        }
+    }
+    MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    // the launches enqueued after the stop flag went up did nothing: the newest slot holds the final scalars
+    const double* fs = hslot[8 + SC_ITER] >= hslot[SC_ITER] ? hslot + 8 : hslot;
+    *iters = (int)fs[SC_ITER];
+    return MFB_OK;
+}
+
 int ensure_scalars(mfb_ctx* ctx) {
-    if (!ctx->scal.p) {
-        MFB_CUDA(ctx->scal.alloc(64 + (size_t)MAXD * RED_BLOCKS));
-        MFB_CUDA(cudaMallocHost((void**)&ctx->h_scal, 64 * sizeof(double)));
+    // partial sums: MAXD dots x RED_BLOCKS blocks for the vector kernels, one per CTA for the SpMV with a fused dot
+    const size_t need = 64 + std::max((size_t)MAXD * RED_BLOCKS, (size_t)(ctx->N / 32 + 2));
+    if (!ctx->scal.p || ctx->scal.n < need) MFB_CUDA(ctx->scal.alloc(need));
+    if (!ctx->h_scal) MFB_CUDA(cudaMallocHost((void**)&ctx->h_scal, 64 * sizeof(double)));
+    if (!ctx->red_counter.p) {
+        MFB_CUDA(ctx->red_counter.alloc(4));
+        MFB_CUDA(cudaMemsetAsync(ctx->red_counter.p, 0, 4 * sizeof(unsigned), ctx->stream));
     }
     return MFB_OK;
 }
@@ -1353,7 +2014,7 @@ extern "C" int mfb_krylov_solve_ex(mfb_ctx* ctx, int method, int s, int maxiter,
     }
     const int nvec = nw + 3;  // + x, r, (spare)
     MFB_TRY(ensure_work(ctx, nvec, n));
-    DevBuf<double> Ks;  // scaled matrix copy, freed on return (the reference allocates K_vals per solve too)
+    DevBuf<double>& Ks = ctx->Ks;  // scaled matrix copy: allocated once and kept across solves (the reference allocates K_vals per solve)
     DevBuf<double> plv; // Pl_Jacobi vector
     MFB_CUDA(Ks.alloc(nval));
     MFB_CUDA(ctx->jac.alloc(n));
@@ -1411,12 +2072,17 @@ extern "C" int mfb_krylov_solve_ex(mfb_ctx* ctx, int method, int s, int maxiter,
     }
     int pass = 1;
     double res = inf.initial_residual, tol_factor = 1.0;
+    const char* lenv = getenv("MFB_KRYLOV_LEGACY");
+    const bool legacy = lenv && lenv[0] == '1';       // round-1 launch structure (A/B measurements)
     while (true) {
         int it = 0;
         const double ptol = tol_factor * tol;
         switch (method) {
             case MFB_IDRS: MFB_TRY(idrs(S, x, b, r, ptol, maxiter, s, seed, pass, W, &it)); break;
-            case MFB_BICGSTABL_GS: MFB_TRY(bicgstabl_gs(S, x, b, r, ptol, maxiter, s, seed, pass, W, &it)); break;
+            case MFB_BICGSTABL_GS:
+                if (legacy) MFB_TRY(bicgstabl_gs_legacy(S, x, b, r, ptol, maxiter, s, seed, pass, W, &it));
+                else MFB_TRY(bicgstabl_gs(S, x, b, r, ptol, maxiter, s, seed, pass, W, &it));
+                break;
             case MFB_BICGSTABL: MFB_TRY(bicgstabl_lu(S, x, b, r, ptol, maxiter, s, seed, pass, W, &it)); break;
             case MFB_GMRES: MFB_TRY(gmres(S, x, b, r, ptol, maxiter, s, W, &it)); break;
             case MFB_CGS: MFB_TRY(cgs(S, x, b, r, ptol, maxiter, W, &it)); break;
@@ -1450,7 +2116,6 @@ extern "C" int mfb_krylov_solve_ex(mfb_ctx* ctx, int method, int s, int maxiter,
         tmp.release();
     }
     MFB_CUDA(cudaStreamSynchronize(ctx->stream));
-    Ks.release();
     plv.release();
     MFB_TRY(mfb_p2p_check(ctx));
     if (info) *info = inf;
@@ -1493,10 +2158,17 @@ extern "C" int mfb_spmv_variant_bench(mfb_ctx* ctx, int variant, int reps, doubl
             case 11: LAUNCH((k_spmv_bsr_x<3, 4, 64>), g(64), 256, np, nc, K, x, y, N); break;
             case 12: LAUNCH((k_spmv_bsr_x<3, 3, 64>), g(64), 256, np, nc, K, x, y, N); break;
             case 13: LAUNCH((k_spmv_bsr_x<3, 5, 128>), g(128), 256, np, nc, K, x, y, N); break;
+            // multi-row streams: RW rows per warp (8 warps per CTA), register cap for 4 / 5 CTAs per SM, unroll 5 / 4 / 6
+            case 14: LAUNCH((k_spmv_mr<3, 5, 8, false, 4>), g(64), 256, np, nc, K, x, y, N, (const double*)nullptr, null_redctx(), ScOp{OP_NONE, 0, 0, 0}); break;
+            case 15: LAUNCH((k_spmv_mr<3, 5, 4, false, 4>), g(32), 256, np, nc, K, x, y, N, (const double*)nullptr, null_redctx(), ScOp{OP_NONE, 0, 0, 0}); break;
+            case 16: LAUNCH((k_spmv_mr<3, 5, 16, false, 4>), g(128), 256, np, nc, K, x, y, N, (const double*)nullptr, null_redctx(), ScOp{OP_NONE, 0, 0, 0}); break;
+            case 17: LAUNCH((k_spmv_mr<3, 5, 8, false, 5>), g(64), 256, np, nc, K, x, y, N, (const double*)nullptr, null_redctx(), ScOp{OP_NONE, 0, 0, 0}); break;
+            case 18: LAUNCH((k_spmv_mr<3, 4, 8, false, 5>), g(64), 256, np, nc, K, x, y, N, (const double*)nullptr, null_redctx(), ScOp{OP_NONE, 0, 0, 0}); break;
+            case 19: LAUNCH((k_spmv_mr<3, 6, 8, false, 4>), g(64), 256, np, nc, K, x, y, N, (const double*)nullptr, null_redctx(), ScOp{OP_NONE, 0, 0, 0}); break;
             default: break;
         }
     };
-    MFB_REQUIRE(variant >= 0 && variant <= 13, MFB_ERR_ARG, "unknown SpMV variant");
+    MFB_REQUIRE(variant >= 0 && variant <= 19, MFB_ERR_ARG, "unknown SpMV variant");
     for (int i = 0; i < 3; ++i) launch(variant);
     MFB_CUDA(cudaEventRecord(e0, ctx->stream));
     for (int i = 0; i < reps; ++i) launch(variant);
@@ -1531,11 +2203,12 @@ extern "C" int mfb_spmv(mfb_ctx* ctx, int which, const double* x, double* y, int
     MFB_TRY(mfb_to_internal(ctx, xr.p, xi.p, 1));
     const double* K = which == MFB_MAT_K_LINEAR ? ctx->K_linear.p : ctx->K_total.p;
     MFB_TRY(mfb_spmv_internal(ctx, K, xi.p, yi.p));
+    MFB_TRY(mfb_halo_add(ctx, yi.p, ctx->n_var));            // partitioned mesh: complete the interface rows
     MFB_TRY(mfb_to_reference(ctx, yi.p, yr.p, 1));
     MFB_TRY(mfb_stage_out(ctx, yr.p, n * sizeof(double), y));
     MFB_CUDA(cudaStreamSynchronize(ctx->stream));
     xr.release(); xi.release(); yi.release(); yr.release();
-    return MFB_OK;
+    return mfb_p2p_check(ctx);
 }
 
 // ---- time stepping helpers (04_Time_Domain.jl) ------------------------------------------------
@@ -1622,5 +2295,5 @@ extern "C" int mfb_residue_norm(mfb_ctx* ctx, double* out) {
     double d;
     MFB_TRY(S.dot1(ctx->residue.p, ctx->residue.p, &d));
     *out = S.nn(d);
-    return MFB_OK;
+    return mfb_p2p_check(ctx);
 }

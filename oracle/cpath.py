@@ -1,5 +1,6 @@
 """ORACLE: ctypes front of c/refpath.c (OpenMP loop nests of the reference's kernels; CPU baseline)."""
 import ctypes as C
+import time
 
 import numpy as np
 
@@ -49,6 +50,8 @@ def res_basic(itp, slot, vals, shift, cp, el, host, residue):
 class CsrOperator:
     """A @ x through the OpenMP CSR kernel (1-based arrays of GlobalField)."""
 
+    calls, seconds = 0, 0.0      # class-wide counters (bench.py's cpu_baseline sub-metrics)
+
     def __init__(self, ptr, col, val, n):
         self.ptr = np.ascontiguousarray(ptr, dtype=np.int32)
         self.col = np.ascontiguousarray(col, dtype=np.int32)
@@ -58,5 +61,8 @@ class CsrOperator:
     def __matmul__(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.empty(self.shape[0])
+        t0 = time.perf_counter()
         _lib().ora_spmv_csr(C.c_int64(self.shape[0]), _p(self.ptr), _p(self.col), _p(self.data), _p(x), _p(y))
+        CsrOperator.seconds += time.perf_counter() - t0
+        CsrOperator.calls += 1
         return y
