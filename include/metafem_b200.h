@@ -143,9 +143,14 @@ int mfb_boundary_group_set(mfb_ctx *ctx, int bg_ID, int64_t n, const int32_t *fa
 int mfb_pattern_build(mfb_ctx *ctx, int n_var, int max_time_level, int n_blocks,
                       const int32_t *sparse_mapping, int64_t *nnz, int64_t *sparse_unitsize);
 /* Reference-layout copies for parity: K_I, K_J [nnz] (sorted by row then column, 1-based),
- * K_J_ptr [n+1] (1-based), K_val_ids [nnz], sparse_IDs_by_el [n_a, n_a, n_el] (CSR position of
- * block 0, 1-based; add m*... via mfb_block_entry_shift). Any pointer may be NULL. */
+ * K_J_ptr [n+1] (1-based), K_val_ids [nnz] (identity, see above). Any pointer may be NULL. */
 int mfb_pattern_get(mfb_ctx *ctx, int32_t *K_I, int32_t *K_J, int32_t *K_J_ptr, int32_t *K_val_ids);
+/* elements.sparse_IDs_by_el [n_a, n_a, n_el] (03_GlobalAssembly.jl:111-118; row = dual node a, column = base node b, elements
+ * in the caller's order) for variable block `block` (index into sparse_mapping): the 1-based position, in the arrays of
+ * mfb_pattern_get / mfb_matrix_get, of the entry that node pair (a, b) of element e accumulates into. The reference's
+ * entry ID `sparse_IDs_by_el[a,b,e] + block * sparse_unitsize` (06_FEM_Kernel.jl:36) addresses its hash-ordered value
+ * array; through K_val_ids it names the same CSR position, which is what this getter returns directly. */
+int mfb_sparse_ids_get(mfb_ctx *ctx, int block, int32_t *sparse_IDs_by_el);
 
 /* ---- fields ------------------------------------------------------------------------------
  * CONTROLPOINT_VAR external fields (controlpoints.<sym>, 05_CodeGenerator.jl:28-35), by local symbol. */
@@ -256,7 +261,7 @@ int mfb_krylov_solve(mfb_ctx *ctx, int method, int s, int maxiter, int max_pass,
 /* Same with the preconditioner choices of iterative_Solve!: Pr_func! in {Pr_Jacobi!, Pr_Jacobi!(normalized_by_column),
  * Identity}, Pl_func in {Identity, Pl_Jacobi, Pl_Jacobi(normalized_by_row)}; with a left preconditioner the per-pass
  * tolerance is rescaled by min(||Pl r|| / ||r||, 1) (:50-53). checkiter: residual check period of tfqmr!.
- * Pl_ILU (cuSPARSE ilu02!, :179-194) is not provided. */
+ * Pl_ILU: see MFB_PL_ILU. */
 int mfb_krylov_solve_ex(mfb_ctx *ctx, int method, int s, int maxiter, int max_pass, double tol, uint64_t seed,
                         int pr_mode, int pl_mode, int checkiter, double *delta_out, mfb_solve_info *info);
 

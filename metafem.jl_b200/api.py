@@ -140,6 +140,13 @@ class FEM_Domain:
         self.ctx.call("mfb_pattern_get", L.ptr(K_I), L.ptr(K_J), L.ptr(K_J_ptr), L.ptr(K_val_ids))
         return K_I, K_J, K_J_ptr, K_val_ids
 
+    def get_sparse_IDs_by_el(self, block=0):
+        """elements.sparse_IDs_by_el [n_a, n_a, n_el] of one variable block: 1-based CSR position of every element node pair."""
+        n_a, n_el = self.tables.controlpoint_IDs.shape
+        out = np.empty((n_a, n_a, n_el), np.int32, order="F")
+        self.ctx.call("mfb_sparse_ids_get", int(block), L.ptr(out))
+        return out
+
     def sync_fields(self):
         """Push controlpoints.<CONTROLPOINT_VAR> and physics.global_vars to the device (read at call time in the reference)."""
         for v in self.spec["cp_vars"]:

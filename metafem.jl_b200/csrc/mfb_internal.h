@@ -62,6 +62,10 @@ struct DevBuf {
     }
 };
 
+// The TMA-ring SpMV copies whole stages of the value / column streams: the last stage of the last rows reads up to this many
+// node-pair entries past the end of the arrays, so nodecol and every matrix value array carry that much slack.
+constexpr int MFB_STREAM_PAD = 1024;
+
 struct BlockKernels {
     int kind = 0, bg_ID = 0;
     cudaKernel_t lin = nullptr, nonlin = nullptr, eval = nullptr;
@@ -201,6 +205,7 @@ int mfb_to_reference(mfb_ctx* ctx, const double* int_vec, double* ref_vec, int l
 int mfb_field_to_internal(mfb_ctx* ctx, const double* ref_field, double* int_field);
 int mfb_export_matrix(mfb_ctx* ctx, const double* Kint, double* Kref_dev);
 int mfb_export_pattern(mfb_ctx* ctx, int* K_I, int* K_J, int* K_J_ptr, int* K_val_ids);  // device ptrs (nullable)
+int mfb_export_sparse_ids(mfb_ctx* ctx, int block, int* out_dev);
 
 // ---- peer-memory mailboxes of the scalar-batch allreduce (mfb_dist.cu owns them; the reduction epilogues of mfb_krylov.cu
 // publish into / read from them) ----

@@ -677,6 +677,7 @@ __global__ void __launch_bounds__(256) k_fused(const Fused* __restrict__ Fg, con
     if (stopped(R)) return;
     __shared__ Fused F;
     __shared__ double s_c[FU_MAXT], s_ay[FU_MAXU], s_w[8];
+    __shared__ int s_single;
     const int tid = threadIdx.x;
     {
         const unsigned long long* src = reinterpret_cast<const unsigned long long*>(Fg);
@@ -686,54 +687,94 @@ __global__ void __launch_bounds__(256) k_fused(const Fused* __restrict__ Fg, con
     __syncthreads();
     if (tid < F.n_term) s_c[tid] = F.t[tid].cp ? F.t[tid].c * __ldcg(F.t[tid].cp) : F.t[tid].c;
     if (tid < F.n_upd) s_ay[tid] = F.u[tid].ayp ? F.u[tid].ay * __ldcg(F.u[tid].ayp) : F.u[tid].ay;
+    if (tid == 0) {
+        int single = 1;
+        for (int u = 0; u < F.n_upd; ++u) single &= (F.u[u].nt == 1);
+        s_single = single;
+    }
     __syncthreads();
     double acc[ND > 0 ? ND : 1];
 #pragma unroll
     for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
     const int64_t np = (n + 1) >> 1;                      // element pairs: 128-bit loads and stores
     const int64_t stride = (int64_t)gridDim.x * 256;
-    for (int64_t p0 = blockIdx.x * (int64_t)256 + tid; p0 < np; p0 += 2 * stride) {
-        const int64_t p1 = p0 + stride;
-        const bool ok1 = p1 < np;
-        double2 r0 = make_double2(0.0, 0.0), r1 = make_double2(0.0, 0.0);
-        for (int u = 0; u < F.n_upd; ++u) {
-            double* yp = F.u[u].y;
-            const double ay = s_ay[u];
-            double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
-            if (ay != 0.0) {
-                a0 = ld2(yp, p0, n);
-                if (ok1) a1 = ld2(yp, p1, n);
-                a0.x *= ay; a0.y *= ay; a1.x *= ay; a1.y *= ay;
+    const bool single = s_single != 0;
+    const double2 zero2 = make_double2(0.0, 0.0);
+    for (int64_t p0 = blockIdx.x * (int64_t)256 + tid; p0 < np; p0 += stride) {
+        double2 r0 = zero2;                               // result of the last update (dot operand)
+        if (single) {
+            // independent single-term updates y_u = ay_u y_u + c_u x_u (the BiCG part): four at a time, eight loads in flight
+            for (int u0 = 0; u0 < F.n_upd; u0 += 4) {
+                double2 yv[4], xv[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int u = u0 + g;
+                    const bool live = u < F.n_upd;
+                    yv[g] = (live && s_ay[u] != 0.0) ? ld2(F.u[u].y, p0, n) : zero2;
+                    xv[g] = live ? ld2(F.t[F.u[u].t0].x, p0, n) : zero2;
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int u = u0 + g;
+                    if (u < F.n_upd) {
+                        const double ay = s_ay[u], c = s_c[F.u[u].t0];
+                        r0 = make_double2(ay * yv[g].x + c * xv[g].x, ay * yv[g].y + c * xv[g].y);
+                        st2(F.u[u].y, p0, n, r0);
+                    }
+                }
             }
-            const int t1 = F.u[u].t0 + F.u[u].nt;
-            for (int t = F.u[u].t0; t < t1; ++t) {
-                const double c = s_c[t];
-                const double* xp = F.t[t].x;
-                const double2 x0 = ld2(xp, p0, n);
-                const double2 x1 = ok1 ? ld2(xp, p1, n) : make_double2(0.0, 0.0);
-                a0.x += c * x0.x; a0.y += c * x0.y; a1.x += c * x1.x; a1.y += c * x1.y;
+        } else {
+            for (int u = 0; u < F.n_upd; ++u) {
+                double* yp = F.u[u].y;
+                const double ay = s_ay[u];
+                double2 a0 = (ay != 0.0) ? ld2(yp, p0, n) : zero2;
+                const int t0 = F.u[u].t0, t1 = t0 + F.u[u].nt;
+                double2 xv[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) xv[g] = (t0 + g < t1) ? ld2(F.t[t0 + g].x, p0, n) : zero2;
+                a0.x *= ay; a0.y *= ay;
+                for (int t = t0; t < t1; t += 4) {                       // four term loads in flight, the next four issued before use
+                    double2 xn[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) xn[g] = (t + 4 + g < t1) ? ld2(F.t[t + 4 + g].x, p0, n) : zero2;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        if (t + g < t1) {
+                            const double c = s_c[t + g];
+                            a0.x += c * xv[g].x; a0.y += c * xv[g].y;
+                        }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) xv[g] = xn[g];
+                }
+                st2(yp, p0, n, a0);
+                r0 = a0;
             }
-            st2(yp, p0, n, a0);
-            if (ok1) st2(yp, p1, n, a1);
-            r0 = a0; r1 = a1;
         }
         if constexpr (ND > 0) {
-            double2 w0 = make_double2(1.0, 2 * p0 + 1 < n ? 1.0 : 0.0), w1 = make_double2(ok1 ? 1.0 : 0.0, (ok1 && 2 * p1 + 1 < n) ? 1.0 : 0.0);
+            double2 w0 = make_double2(1.0, 2 * p0 + 1 < n ? 1.0 : 0.0);
             if (owned != nullptr) {                         // count every node once (on its owner)
                 w0.x = owned[(2 * p0) / nv] ? 1.0 : 0.0;
                 if (w0.y != 0.0) w0.y = owned[(2 * p0 + 1) / nv] ? 1.0 : 0.0;
-                if (w1.x != 0.0) w1.x = owned[(2 * p1) / nv] ? 1.0 : 0.0;
-                if (w1.y != 0.0) w1.y = owned[(2 * p1 + 1) / nv] ? 1.0 : 0.0;
             }
+            constexpr int DG = ND < 4 ? ND : 4;
 #pragma unroll
-            for (int d = 0; d < ND; ++d)
-                if (d < F.n_dot) {
-                    const double* xp = F.dx[d];
-                    const double* yp = F.dy[d];
-                    const double2 x0 = xp ? ld2(xp, p0, n) : r0, x1 = xp ? (ok1 ? ld2(xp, p1, n) : make_double2(0.0, 0.0)) : r1;
-                    const double2 y0 = yp ? ld2(yp, p0, n) : r0, y1 = yp ? (ok1 ? ld2(yp, p1, n) : make_double2(0.0, 0.0)) : r1;
-                    acc[d] += (w0.x * (x0.x * y0.x) + w0.y * (x0.y * y0.y)) + (w1.x * (x1.x * y1.x) + w1.y * (x1.y * y1.y));
+            for (int d0 = 0; d0 < ND; d0 += DG) {
+                if (d0 < F.n_dot) {
+                    double2 xv[DG], yv[DG];
+#pragma unroll
+                    for (int g = 0; g < DG; ++g) {
+                        const int d = d0 + g;
+                        const bool live = d < F.n_dot;
+                        const double* xp = live ? F.dx[d] : nullptr;
+                        const double* yp = live ? F.dy[d] : nullptr;
+                        xv[g] = xp ? ld2(xp, p0, n) : r0;
+                        yv[g] = yp ? (yp == xp ? xv[g] : ld2(yp, p0, n)) : r0;
+                    }
+#pragma unroll
+                    for (int g = 0; g < DG; ++g)
+                        if (d0 + g < F.n_dot) acc[d0 + g] += w0.x * (xv[g].x * yv[g].x) + w0.y * (xv[g].y * yv[g].y);
                 }
+            }
         }
     }
     if constexpr (ND > 0) {
@@ -753,110 +794,310 @@ __global__ void __launch_bounds__(256) k_fused(const Fused* __restrict__ Fg, con
 // five). Row boundaries inside a batch are resolved with predicated adds on the (rare) slow path; a batch that lies inside one
 // row takes the FMA fast path. With DOT the kernel also accumulates sum_rows w[row] . y[row] (the dot product the Krylov
 // method takes of the fresh product: r_shadow' A u) and finishes it in its tail: no second pass over y, no extra launch.
+// the stream loop of one warp (its RW consecutive rows)
+template <int NV, int UNR, int RW>
+__device__ __forceinline__ void spmv_mr_rows(const int* __restrict__ nodeptr, const int* __restrict__ nodecol, const double* __restrict__ K,
+                                          const double* __restrict__ x, double* __restrict__ y, int64_t N, int64_t row0) {
+    constexpr int B = NV * NV, EPW = 32 / B, ACTIVE = EPW * B, W = UNR * EPW;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int le = lane / B, ik = lane - le * B, i = ik / NV, k = ik - i * NV;
+    const bool on = lane < ACTIVE;
+    const double* xk = x + k;
+    const int nr = (int)min((int64_t)RW, N - row0);
+    const int myp = (lane <= nr) ? __ldg(nodeptr + row0 + lane) : 0;     // lane l holds nodeptr[row0 + l]
+    const int s = __shfl_sync(FULL, myp, 0);
+    const int degw = __shfl_sync(FULL, myp, nr) - s;                     // length of the whole stream (warp-uniform)
+    const int deg = on ? degw : 0;
+    int cr = 0, lo = 0, hi = __shfl_sync(FULL, myp, 1) - s;              // current row and its entry range within the stream
+    const double* Kp = K + (size_t)s * B + lane;
+    const int* Cp = nodecol + s + le;
+    double a[UNR], v[UNR];
+    int c[UNR];
+    int e = le, base = 0;
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+        a[u] = 0.0;
+        const bool ok = e + u * EPW < deg;
+        v[u] = ok ? __ldcs(Kp + u * ACTIVE) : 0.0;
+        c[u] = ok ? __ldg(Cp + u * EPW) : 0;
+    }
+    for (;;) {
+        double vn[UNR];
+        int cn[UNR];
+        Kp += UNR * ACTIVE;
+        Cp += UNR * EPW;
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {                                  // streams of the NEXT batch first ...
+            const bool ok = e + W + u * EPW < deg;
+            vn[u] = ok ? __ldcs(Kp + u * ACTIVE) : 0.0;
+            cn[u] = ok ? __ldg(Cp + u * EPW) : 0;
+        }
+        double xg[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) xg[u] = __ldg(xk + (size_t)c[u] * NV);   // ... then the dependent gathers of this one
+        const int bend = base + W;
+        if (bend < hi) {                                                  // the whole batch lies inside row cr
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) a[u] = fma(v[u], xg[u], a[u]);
+        } else {                                                          // the batch reaches the end of row cr
+            double p[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) p[u] = v[u] * xg[u];
+            for (;;) {
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int eu = e + u * EPW;
+                    if (eu >= lo && eu < hi) a[u] += p[u];
+                }
+                double acc = 0.0;
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) { acc += a[u]; a[u] = 0.0; }
+                double t = acc;
+#pragma unroll
+                for (int d = 1; d < NV; ++d) t += __shfl_down_sync(FULL, acc, d);           // sum over k
+                double r = t;
+                if constexpr ((B & (B - 1)) == 0) {
+#pragma unroll
+                    for (int o = 16; o >= B; o >>= 1) r += __shfl_xor_sync(FULL, r, o);
+                } else {
+#pragma unroll
+                    for (int d = 1; d < EPW; ++d) r += __shfl_down_sync(FULL, t, d * B);    // sum over the EPW entries
+                }
+                if (le == 0 && k == 0 && on) y[(size_t)(row0 + cr) * NV + i] = r;
+                ++cr;
+                lo = hi;
+                if (cr >= nr) break;
+                hi = __shfl_sync(FULL, myp, cr + 1) - s;
+                if (bend < hi) {                                          // row cr goes on in later batches: take its share of this one
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u)
+                        if (e + u * EPW >= lo) a[u] += p[u];
+                    break;
+                }
+            }
+            if (cr >= nr) break;
+        }
+        base = bend;
+        e += W;
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) { v[u] = vn[u]; c[u] = cn[u]; }
+    }
+}
+
+// ---- SpMV, TMA ring: the value / column streams of a warp's RW rows are pulled into a warp-private shared-memory ring by
+// cp.async.bulk (1-D TMA) copies that complete on mbarriers, NSTG stages of E entries ahead of the consumer. The stream no
+// longer occupies registers or waits for the gathers: the bytes in flight per SM are set by the ring (2 CTAs x 8 warps x 2
+// stages x 4.5 kB = 146 kB for NV = 3) instead of by warps x unroll (43 kB in k_spmv_bsr, which measured at the 5.6 TB/s that
+// 43 kB per SM and ~1.1 us of loaded DRAM latency allow). The consumer reads values and column ids from shared memory and
+// keeps the x gathers of the NEXT batch in flight while it multiplies the current one.
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_addr(b))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try(unsigned long long* b, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_addr(b)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    for (long long spins = 0; !mbar_try(b, parity); ++spins)
+        if (spins > (1ll << 26)) __trap();                 // a copy that never lands must not hang the GPU
+}
+
+template <int NV, int UNR> struct TmaStage {
+    static constexpr int B = NV * NV, EPW = 32 / B, W = UNR * EPW;
+    static constexpr int NB = (W % 4 == 0) ? 4 : 4;        // batches per stage
+    static constexpr int E = NB * W;                       // entries per stage (multiple of 4: 16-byte aligned copies)
+    static constexpr int VB = E * B * 8, CB = E * 4, SB = VB + CB;
+    static_assert(E % 4 == 0 && VB % 16 == 0 && CB % 16 == 0, "bulk copies need 16-byte granularity");
+};
+
+template <int NV, int UNR, int RW, int NSTG, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_spmv_tma(const int* __restrict__ nodeptr, const int* __restrict__ nodecol,
+                                                         const double* __restrict__ K, const double* __restrict__ x,
+                                                         double* __restrict__ y, int64_t N, const double* __restrict__ sc) {
+    if (sc != nullptr && *reinterpret_cast<const volatile double*>(sc + SC_STOP) != 0.0) return;
+    using T = TmaStage<NV, UNR>;
+    constexpr int B = T::B, EPW = T::EPW, ACTIVE = EPW * B, W = T::W, NB = T::NB, E = T::E, VB = T::VB, SB = T::SB;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* ring = tma_smem + (size_t)warp * NSTG * SB;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(tma_smem + (size_t)WARPS * NSTG * SB) + warp * NSTG;
+    if (lane == 0)
+        for (int q = 0; q < NSTG; ++q) mbar_init(bars + q, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    const int64_t row0 = (blockIdx.x * (int64_t)WARPS + warp) * RW;
+    if (row0 >= N) return;
+    const int le = lane / B, ik = lane - le * B, i = ik / NV, k = ik - i * NV;
+    const bool on = lane < ACTIVE;
+    const double* xk = x + k;
+    const int nr = (int)min((int64_t)RW, N - row0);
+    const int myp = (lane <= nr) ? __ldg(nodeptr + row0 + lane) : 0;     // lane l holds nodeptr[row0 + l]
+    const int s = __shfl_sync(FULL, myp, 0);
+    const int degw = __shfl_sync(FULL, myp, nr) - s;                     // entries of the warp's stream
+    if (degw <= 0) {
+        if (lane < nr * NV) y[(size_t)row0 * NV + lane] = 0.0;
+        return;
+    }
+    const int lead = s & 3;                                              // the copies start at a multiple of 4 entries
+    const size_t a0 = (size_t)(s - lead);
+    const int nstg = (lead + degw + E - 1) / E, nq = nstg * NB;
+    auto issue = [&](int g) {                                            // stage g of the stream -> ring slot g % NSTG
+        if (lane == 0) {
+            const int slot = g % NSTG;
+            const size_t e0 = a0 + (size_t)g * E;
+            mbar_expect(bars + slot, (unsigned)SB);
+            bulk_g2s(ring + (size_t)slot * SB, K + e0 * B, (unsigned)VB, bars + slot);
+            bulk_g2s(ring + (size_t)slot * SB + VB, nodecol + e0, (unsigned)T::CB, bars + slot);
+        }
+    };
+    for (int g = 0; g < NSTG && g < nstg; ++g) issue(g);
+    int cr = 0, lo = 0, hi = __shfl_sync(FULL, myp, 1) - s;              // current row and its entry range (relative to s)
+    double a[UNR], xg[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) a[u] = 0.0;
+    // gathers of batch q: entries (relative to s) q * W - lead + le + u * EPW
+    auto gather = [&](int q, double (&xo)[UNR]) {
+        const int g = q / NB, b = q - g * NB;
+        const int* Cs = reinterpret_cast<const int*>(ring + (size_t)(g % NSTG) * SB + VB) + b * W + le;
+        const int e = q * W - lead + le;
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int eu = e + u * EPW;
+            const bool ok = on && eu >= 0 && eu < degw;
+            const int c = ok ? Cs[u * EPW] : 0;
+            xo[u] = __ldg(xk + (size_t)c * NV);
+        }
+    };
+    mbar_wait(bars, 0);
+    gather(0, xg);
+    for (int q = 0; q < nq; ++q) {
+        const int g = q / NB, b = q - g * NB;
+        double xn[UNR];
+        if (q + 1 < nq) {
+            if (b == NB - 1) mbar_wait(bars + (g + 1) % NSTG, (unsigned)(((g + 1) / NSTG) & 1));
+            gather(q + 1, xn);
+        }
+        const double* Vs = reinterpret_cast<const double*>(ring + (size_t)(g % NSTG) * SB) + (size_t)(b * W) * B + lane;
+        const int e = q * W - lead + le;
+        double p[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int eu = e + u * EPW;
+            const bool ok = on && eu >= 0 && eu < degw;
+            p[u] = ok ? Vs[u * ACTIVE] * xg[u] : 0.0;
+        }
+        const int bend = q * W - lead + W;
+        if (bend < hi) {
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) a[u] += p[u];
+        } else {
+            for (;;) {
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int eu = e + u * EPW;
+                    if (eu >= lo && eu < hi) a[u] += p[u];
+                }
+                double acc = 0.0;
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) { acc += a[u]; a[u] = 0.0; }
+                double t = acc;
+#pragma unroll
+                for (int d = 1; d < NV; ++d) t += __shfl_down_sync(FULL, acc, d);
+                double r = t;
+                if constexpr ((B & (B - 1)) == 0) {
+#pragma unroll
+                    for (int o = 16; o >= B; o >>= 1) r += __shfl_xor_sync(FULL, r, o);
+                } else {
+#pragma unroll
+                    for (int d = 1; d < EPW; ++d) r += __shfl_down_sync(FULL, t, d * B);
+                }
+                if (le == 0 && k == 0 && on) y[(size_t)(row0 + cr) * NV + i] = r;
+                ++cr;
+                lo = hi;
+                if (cr >= nr) break;
+                hi = __shfl_sync(FULL, myp, cr + 1) - s;
+                if (bend < hi) {
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u)
+                        if (e + u * EPW >= lo) a[u] += p[u];
+                    break;
+                }
+            }
+        }
+        if (b == NB - 1) {                                               // stage g is consumed: refill its slot
+            __syncwarp();
+            if (g + NSTG < nstg) issue(g + NSTG);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) xg[u] = xn[u];
+        if (cr >= nr) break;
+    }
+}
+
 template <int NV, int UNR, int RW, bool DOT, int MINB = 0>
 __global__ void __launch_bounds__(256, MINB) k_spmv_mr(const int* __restrict__ nodeptr, const int* __restrict__ nodecol,
                                                  const double* __restrict__ K, const double* __restrict__ x,
                                                  double* __restrict__ y, int64_t N, const double* __restrict__ wdot,
-                                                 const RedCtx R, const ScOp op0) {
-    if (stopped(R)) return;
-    constexpr int B = NV * NV, EPW = 32 / B, ACTIVE = EPW * B, W = UNR * EPW;
-    constexpr unsigned FULL = 0xffffffffu;
+                                                 double* __restrict__ sc, double* __restrict__ red, double* __restrict__ partials,
+                                                 unsigned* __restrict__ counter, const int opcode) {
+    if (sc != nullptr && *reinterpret_cast<const volatile double*>(sc + SC_STOP) != 0.0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int le = lane / B, ik = lane - le * B, i = ik / NV, k = ik - i * NV;
-    const bool on = lane < ACTIVE;
-    const double* xk = x + k;
     double dacc = 0.0;
     const int64_t row0 = (blockIdx.x * (int64_t)8 + warp) * RW;
     if (row0 < N) {
-        const int nr = (int)min((int64_t)RW, N - row0);
-        const int myp = (lane <= nr) ? __ldg(nodeptr + row0 + lane) : 0;     // lane l holds nodeptr[row0 + l]
-        const int s = __shfl_sync(FULL, myp, 0);
-        const int degw = __shfl_sync(FULL, myp, nr) - s;                     // length of the whole stream (warp-uniform)
-        const int deg = on ? degw : 0;
-        int cr = 0, lo = 0, hi = __shfl_sync(FULL, myp, 1) - s;              // current row and its entry range within the stream
-        const double* Kp = K + (size_t)s * B + lane;
-        const int* Cp = nodecol + s + le;
-        double a[UNR], v[UNR];
-        int c[UNR];
-        int e = le, base = 0;
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            a[u] = 0.0;
-            const bool ok = e + u * EPW < deg;
-            v[u] = ok ? __ldcs(Kp + u * ACTIVE) : 0.0;
-            c[u] = ok ? __ldg(Cp + u * EPW) : 0;
-        }
-        for (;;) {
-            double vn[UNR];
-            int cn[UNR];
-            Kp += UNR * ACTIVE;
-            Cp += UNR * EPW;
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {                                  // streams of the NEXT batch first ...
-                const bool ok = e + W + u * EPW < deg;
-                vn[u] = ok ? __ldcs(Kp + u * ACTIVE) : 0.0;
-                cn[u] = ok ? __ldg(Cp + u * EPW) : 0;
+        spmv_mr_rows<NV, UNR, RW>(nodeptr, nodecol, K, x, y, N, row0);
+        if constexpr (DOT) {
+            // the dot product of the warp's fresh rows: the nr * NV values were written by lanes of this warp a moment ago
+            __syncwarp();
+            const int m = (int)min((int64_t)RW, N - row0) * NV;
+#pragma unroll 1
+            for (int q = lane; q < m; q += 32) {
+                const size_t at = (size_t)row0 * NV + q;
+                dacc += __ldcg(y + at) * __ldg(wdot + at);
             }
-            double xg[UNR];
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) xg[u] = __ldg(xk + (size_t)c[u] * NV);   // ... then the dependent gathers of this one
-            const int bend = base + W;
-            if (bend < hi) {                                                  // the whole batch lies inside row cr
-#pragma unroll
-                for (int u = 0; u < UNR; ++u) a[u] = fma(v[u], xg[u], a[u]);
-            } else {                                                          // the batch reaches the end of row cr
-                double p[UNR];
-#pragma unroll
-                for (int u = 0; u < UNR; ++u) p[u] = v[u] * xg[u];
-                for (;;) {
-#pragma unroll
-                    for (int u = 0; u < UNR; ++u) {
-                        const int eu = e + u * EPW;
-                        if (eu >= lo && eu < hi) a[u] += p[u];
-                    }
-                    double acc = 0.0;
-#pragma unroll
-                    for (int u = 0; u < UNR; ++u) { acc += a[u]; a[u] = 0.0; }
-                    double t = acc;
-#pragma unroll
-                    for (int d = 1; d < NV; ++d) t += __shfl_down_sync(FULL, acc, d);           // sum over k
-                    double r = t;
-                    if constexpr ((B & (B - 1)) == 0) {
-#pragma unroll
-                        for (int o = 16; o >= B; o >>= 1) r += __shfl_xor_sync(FULL, r, o);
-                    } else {
-#pragma unroll
-                        for (int d = 1; d < EPW; ++d) r += __shfl_down_sync(FULL, t, d * B);    // sum over the EPW entries
-                    }
-                    if (le == 0 && k == 0 && on) {
-                        const size_t at = (size_t)(row0 + cr) * NV + i;
-                        y[at] = r;
-                        if constexpr (DOT) dacc += r * __ldg(wdot + at);
-                    }
-                    ++cr;
-                    lo = hi;
-                    if (cr >= nr) break;
-                    hi = __shfl_sync(FULL, myp, cr + 1) - s;
-                    if (bend < hi) {                                          // row cr goes on in later batches: take its share of this one
-#pragma unroll
-                        for (int u = 0; u < UNR; ++u)
-                            if (e + u * EPW >= lo) a[u] += p[u];
-                        break;
-                    }
-                }
-                if (cr >= nr) break;
-            }
-            base = bend;
-            e += W;
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) { v[u] = vn[u]; c[u] = cn[u]; }
         }
     }
     if constexpr (DOT) {
+        // lean tail (one GPU only: a partitioned product needs its interface rows completed before any dot): per-block partial,
+        // ticket, the last block folds in a fixed order and applies the alpha / beta recurrence (03_BiCGstabl.jl:46-48,54)
         __shared__ double s_w[8];
+        __shared__ int s_last;
         const double w = block_sum256(dacc, s_w);
-        if (threadIdx.x == 0) R.partials[blockIdx.x] = w;
-        reduce_tail(R, 1, op0, ScOp{OP_NONE, 0, 0, 0});
+        if (threadIdx.x == 0) {
+            partials[blockIdx.x] = w;
+            __threadfence();
+            s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            double v = 0.0;
+#pragma unroll 2
+            for (int b = threadIdx.x; b < (int)gridDim.x; b += 256) v += __ldcg(partials + b);
+            const double tot = block_sum256(v, s_w);
+            if (threadIdx.x == 0) {
+                red[0] = tot;
+                if (opcode == OP_ALPHA) {
+                    sc[SC_ALPHA] = sc[SC_RHO0] / tot;
+                } else if (opcode == OP_BETA) {
+                    sc[SC_BETA] = sc[SC_ALPHA] * tot / sc[SC_RHO0];
+                    sc[SC_RHO0] = tot;
+                }
+                *counter = 0u;
+            }
+        }
     }
 }
 
@@ -992,7 +1233,7 @@ int mfb_spmv_kind(mfb_ctx* ctx) {
     static int kind = -1;
     if (kind < 0) {
         const char* e = getenv("MFB_SPMV");
-        kind = (e && (e[0] == 'r' || e[0] == '0')) ? 0 : 1;      // MFB_SPMV=row: one warp per row (round-1 kernel); default: multi-row streams
+        kind = (e && (e[0] == 'r' || e[0] == '0')) ? 0 : (e && e[0] == 't') ? 2 : 1;   // row: one warp per row (round-1 kernel) | tma: TMA ring | default: multi-row streams
     }
     return kind;
 }
@@ -1007,6 +1248,22 @@ int spmv_rw() {
     }
     return rw;
 }
+template <int NV, int RW, int NSTG, int WARPS>
+void launch_tma(mfb_ctx* ctx, const double* K, const double* x, double* y, const double* sc) {
+    constexpr int UNR = SpmvUnroll<NV>::value;
+    using T = TmaStage<NV, UNR>;
+    const int smem = WARPS * NSTG * T::SB + WARPS * NSTG * 8;
+    auto kern = k_spmv_tma<NV, UNR, RW, NSTG, WARPS>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    const int64_t N = ctx->N;
+    const unsigned grid = (unsigned)((N + (int64_t)WARPS * RW - 1) / ((int64_t)WARPS * RW));
+    kern<<<grid, WARPS * 32, smem, ctx->stream>>>(ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N, sc);
+    ctx->launches++;
+}
 RedCtx null_redctx() {
     RedCtx R;
     memset(&R, 0, sizeof(R));
@@ -1019,8 +1276,8 @@ void launch_spmv_mr(mfb_ctx* ctx, const double* K, const double* x, double* y, c
     // the register cap keeps the fused-dot variant at the occupancy of the plain one (its fold / scalar-op tail, executed by one
     // block, may spill instead)
     constexpr int MINB = NV <= 3 ? 4 : (NV == 4 ? 3 : 2);
-    if (w) k_spmv_mr<NV, SpmvUnroll<NV>::value, RW, true, MINB><<<grid, 256, 0, ctx->stream>>>(ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N, w, R, op);
-    else k_spmv_mr<NV, SpmvUnroll<NV>::value, RW, false, MINB><<<grid, 256, 0, ctx->stream>>>(ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N, w, R, op);
+    if (w) k_spmv_mr<NV, SpmvUnroll<NV>::value, RW, true, MINB><<<grid, 256, 0, ctx->stream>>>(ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N, w, R.sc, R.red, R.partials, R.counter, op.op);
+    else k_spmv_mr<NV, SpmvUnroll<NV>::value, RW, false, MINB><<<grid, 256, 0, ctx->stream>>>(ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N, w, R.sc, R.red, R.partials, R.counter, op.op);
     ctx->launches++;
 }
 }  // namespace
@@ -1030,7 +1287,12 @@ void launch_spmv_mr(mfb_ctx* ctx, const double* K, const double* x, double* y, c
 static int spmv_launch(mfb_ctx* ctx, const double* K, const double* x, double* y, const double* w, const RedCtx& R, const ScOp& op) {
     const int64_t N = ctx->N;
     ProfScope ps(ctx, MFB_T_SPMV);
-    if (mfb_spmv_kind(ctx) == 1 && ctx->n_var <= 5) {
+    if (mfb_spmv_kind(ctx) == 2 && ctx->n_var == 3 && w == nullptr) {
+        launch_tma<3, 8, 3, 8>(ctx, K, x, y, R.sc);
+        MFB_CUDA(cudaGetLastError());
+        return MFB_OK;
+    }
+    if (mfb_spmv_kind(ctx) >= 1 && ctx->n_var <= 5) {
         const int rw = spmv_rw();
         switch (ctx->n_var) {
             case 1: launch_spmv_mr<1, 8>(ctx, K, x, y, w, R, op); break;
@@ -1241,7 +1503,12 @@ struct Solver {
     }
     // y = A x with the dot w'y (+ scalar op) fused into the SpMV tail when the product needs no completion by other ranks
     // and no left preconditioner; otherwise SpMV (+ interface exchange, + Pl) followed by the program `dot_prog`
-    bool can_fuse_spmv_dot() const { return mfb_spmv_kind(ctx) == 1 && ctx->n_var <= 5 && !pl && !mfb_is_distributed(ctx); }
+    // (off by default: inlined into the stream loop's kernel the fold tail makes ptxas spill inside the loop under the 4-CTA
+    // register cap -- 3.3 ms instead of 2.2 ms per SpMV measured; MFB_SPMV_DOT=1 re-enables it for experiments)
+    bool can_fuse_spmv_dot() const {
+        static const bool want = [] { const char* e = getenv("MFB_SPMV_DOT"); return e && e[0] == '1'; }();
+        return want && mfb_spmv_kind(ctx) == 1 && ctx->n_var <= 5 && !pl && !mfb_is_distributed(ctx);
+    }
     int mul_dot(double* y, const double* x, const double* w, const ScOp& op, int dot_prog) {
         spmv++;
         if (w && can_fuse_spmv_dot()) {
@@ -2016,7 +2283,7 @@ extern "C" int mfb_krylov_solve_ex(mfb_ctx* ctx, int method, int s, int maxiter,
     MFB_TRY(ensure_work(ctx, nvec, n));
     DevBuf<double>& Ks = ctx->Ks;  // scaled matrix copy: allocated once and kept across solves (the reference allocates K_vals per solve)
     DevBuf<double> plv; // Pl_Jacobi vector
-    MFB_CUDA(Ks.alloc(nval));
+    MFB_CUDA(Ks.alloc(nval + (size_t)MFB_STREAM_PAD * nv * nv));
     MFB_CUDA(ctx->jac.alloc(n));
     MFB_CUDA(ctx->delta.alloc(n));
     std::vector<int> diag_ok(nv);
@@ -2159,16 +2426,21 @@ extern "C" int mfb_spmv_variant_bench(mfb_ctx* ctx, int variant, int reps, doubl
             case 12: LAUNCH((k_spmv_bsr_x<3, 3, 64>), g(64), 256, np, nc, K, x, y, N); break;
             case 13: LAUNCH((k_spmv_bsr_x<3, 5, 128>), g(128), 256, np, nc, K, x, y, N); break;
             // multi-row streams: RW rows per warp (8 warps per CTA), register cap for 4 / 5 CTAs per SM, unroll 5 / 4 / 6
-            case 14: LAUNCH((k_spmv_mr<3, 5, 8, false, 4>), g(64), 256, np, nc, K, x, y, N, (const double*)nullptr, null_redctx(), ScOp{OP_NONE, 0, 0, 0}); break;
-            case 15: LAUNCH((k_spmv_mr<3, 5, 4, false, 4>), g(32), 256, np, nc, K, x, y, N, (const double*)nullptr, null_redctx(), ScOp{OP_NONE, 0, 0, 0}); break;
-            case 16: LAUNCH((k_spmv_mr<3, 5, 16, false, 4>), g(128), 256, np, nc, K, x, y, N, (const double*)nullptr, null_redctx(), ScOp{OP_NONE, 0, 0, 0}); break;
-            case 17: LAUNCH((k_spmv_mr<3, 5, 8, false, 5>), g(64), 256, np, nc, K, x, y, N, (const double*)nullptr, null_redctx(), ScOp{OP_NONE, 0, 0, 0}); break;
-            case 18: LAUNCH((k_spmv_mr<3, 4, 8, false, 5>), g(64), 256, np, nc, K, x, y, N, (const double*)nullptr, null_redctx(), ScOp{OP_NONE, 0, 0, 0}); break;
-            case 19: LAUNCH((k_spmv_mr<3, 6, 8, false, 4>), g(64), 256, np, nc, K, x, y, N, (const double*)nullptr, null_redctx(), ScOp{OP_NONE, 0, 0, 0}); break;
+            case 14: LAUNCH((k_spmv_mr<3, 5, 8, false, 4>), g(64), 256, np, nc, K, x, y, N, (const double*)nullptr, (double*)nullptr, (double*)nullptr, (double*)nullptr, (unsigned*)nullptr, 0); break;
+            case 15: LAUNCH((k_spmv_mr<3, 5, 4, false, 4>), g(32), 256, np, nc, K, x, y, N, (const double*)nullptr, (double*)nullptr, (double*)nullptr, (double*)nullptr, (unsigned*)nullptr, 0); break;
+            case 16: LAUNCH((k_spmv_mr<3, 5, 16, false, 4>), g(128), 256, np, nc, K, x, y, N, (const double*)nullptr, (double*)nullptr, (double*)nullptr, (double*)nullptr, (unsigned*)nullptr, 0); break;
+            case 17: LAUNCH((k_spmv_mr<3, 5, 8, false, 5>), g(64), 256, np, nc, K, x, y, N, (const double*)nullptr, (double*)nullptr, (double*)nullptr, (double*)nullptr, (unsigned*)nullptr, 0); break;
+            case 18: LAUNCH((k_spmv_mr<3, 4, 8, false, 5>), g(64), 256, np, nc, K, x, y, N, (const double*)nullptr, (double*)nullptr, (double*)nullptr, (double*)nullptr, (unsigned*)nullptr, 0); break;
+            case 19: LAUNCH((k_spmv_mr<3, 6, 8, false, 4>), g(64), 256, np, nc, K, x, y, N, (const double*)nullptr, (double*)nullptr, (double*)nullptr, (double*)nullptr, (unsigned*)nullptr, 0); break;
+            case 20: launch_tma<3, 8, 3, 8>(ctx, K, x, y, nullptr); break;
+            case 21: launch_tma<3, 8, 2, 8>(ctx, K, x, y, nullptr); break;
+            case 22: launch_tma<3, 16, 3, 8>(ctx, K, x, y, nullptr); break;
+            case 23: launch_tma<3, 8, 4, 4>(ctx, K, x, y, nullptr); break;
+            case 24: launch_tma<3, 16, 2, 8>(ctx, K, x, y, nullptr); break;
             default: break;
         }
     };
-    MFB_REQUIRE(variant >= 0 && variant <= 19, MFB_ERR_ARG, "unknown SpMV variant");
+    MFB_REQUIRE(variant >= 0 && variant <= 24, MFB_ERR_ARG, "unknown SpMV variant");
     for (int i = 0; i < 3; ++i) launch(variant);
     MFB_CUDA(cudaEventRecord(e0, ctx->stream));
     for (int i = 0; i < reps; ++i) launch(variant);

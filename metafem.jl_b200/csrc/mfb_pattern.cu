@@ -197,6 +197,23 @@ __global__ void k_row_of_entry(const int* nodeptr, int64_t N, int* row_of_entry)
     for (int k = nodeptr[a] + threadIdx.x; k < nodeptr[a + 1]; k += blockDim.x) row_of_entry[k] = (int)a;
 }
 
+// sparse_IDs_by_el[a, b, e] (column-major, e = REFERENCE element): 1-based position, in the exported reference-layout CSR,
+// of the entry that pair (a, b) of element e feeds in variable block (i, k)
+__global__ void k_sparse_ids(const int* emap, const int* elem_rank, const int* nodeptr, const int* iperm, const int* ref_pos,
+                             const int* rowptr_ref, const int* row_of_entry, int n_a, int64_t n_el, int64_t N, int i, int ks, int* out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t per = (int64_t)n_a * n_a;
+    if (t >= per * n_el) return;
+    const int64_t e = t / per;
+    const int p = (int)(t - e * per);
+    const int a = p % n_a, b = p / n_a;                     // output index a + n_a * (b + n_a * e)
+    const int ent = emap[(int64_t)elem_rank[e] * per + a * n_a + b];
+    const int row_node = row_of_entry[ent];
+    const int deg = nodeptr[row_node + 1] - nodeptr[row_node];
+    const int64_t row = iperm[row_node] + (int64_t)i * N;
+    out[t] = rowptr_ref[row] + ks * deg + ref_pos[ent] + 1;
+}
+
 __global__ void k_iota1(int* p, int64_t n) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) p[i] = (int)i + 1;
@@ -284,7 +301,8 @@ int mfb_build_pattern(mfb_ctx* ctx) {
     MFB_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->U = end - kp;
     MFB_REQUIRE(ctx->U < (int64_t)2147483647, MFB_ERR_ARG, "node graph exceeds int32 indexing");
-    MFB_CUDA(ctx->nodecol.alloc(ctx->U));
+    MFB_CUDA(ctx->nodecol.alloc(ctx->U + MFB_STREAM_PAD));
+    MFB_CUDA(cudaMemsetAsync(ctx->nodecol.p + ctx->U, 0, MFB_STREAM_PAD * sizeof(int), ctx->stream));
     MFB_CUDA(ctx->nodeptr.alloc(N + 1));
     LAUNCH(k_split, nblk(ctx->U), TPB, keys.p, ctx->U, ctx->nodecol.p);
     thrust::counting_iterator<int64_t> c0(0);
@@ -388,6 +406,21 @@ int mfb_export_pattern(mfb_ctx* ctx, int* K_I, int* K_J, int* K_J_ptr, int* K_va
         LAUNCH(k_add1, nblk(ctx->N * nv + 1), TPB, K_J_ptr, ctx->N * nv + 1);
     }
     if (K_val_ids) LAUNCH(k_iota1, nblk(nnz), TPB, K_val_ids, nnz);
+    MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MFB_OK;
+}
+
+// sparse_IDs_by_el of one variable block in the reference's table layout (03_GlobalAssembly.jl:111-118): device pointer out
+int mfb_export_sparse_ids(mfb_ctx* ctx, int block, int* out_dev) {
+    RefLayout R;
+    MFB_TRY(build_ref_layout(ctx, R));
+    const int nv = ctx->n_var;
+    const int i = ctx->sparse_mapping[2 * block], k = ctx->sparse_mapping[2 * block + 1];
+    int ks = 0;
+    for (int kk = 0; kk < k; ++kk) ks += ctx->block_of[i * nv + kk] >= 0;
+    const int64_t total = ctx->n_el * ctx->n_a * ctx->n_a;
+    LAUNCH(k_sparse_ids, nblk(total), TPB, ctx->emap.p, ctx->elem_rank.p, ctx->nodeptr.p, ctx->iperm.p, ctx->ref_pos.p, R.rowptr.p,
+           R.row_of_entry.p, ctx->n_a, ctx->n_el, ctx->N, i, ks, out_dev);
     MFB_CUDA(cudaStreamSynchronize(ctx->stream));
     return MFB_OK;
 }

@@ -61,6 +61,7 @@ _SIGS = {
     "mfb_boundary_group_set": (C.c_int, [_P, C.c_int, C.c_int64, _P]),
     "mfb_pattern_build": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mfb_pattern_get": (C.c_int, [_P, _P, _P, _P, _P]),
+    "mfb_sparse_ids_get": (C.c_int, [_P, C.c_int, _P]),
     "mfb_field_set": (C.c_int, [_P, C.c_char_p, _P]),
     "mfb_global_set": (C.c_int, [_P, C.c_char_p, C.c_double]),
     "mfb_vector_set": (C.c_int, [_P, C.c_int, _P, C.c_int64]),

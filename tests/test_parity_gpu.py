@@ -136,3 +136,15 @@ def test_newton_step_parity(pair):
     # converged Newton states agree to the accuracy the tolerances allow (penalty BCs make K ill-conditioned)
     assert ho[-1] < dom.globalfield.converge_tol and hp[-1] < dom.globalfield.converge_tol
     assert np.linalg.norm(xp - xo) / np.linalg.norm(xo) < 1e-4
+
+
+def test_sparse_ids_by_el_match_the_oracle(pair):
+    """elements.sparse_IDs_by_el (03_GlobalAssembly.jl:111-118): the oracle's hash-order entry IDs, taken through K_val_ids to CSR
+    positions, are what mfb_sparse_ids_get returns for every variable block."""
+    dom, fd = pair
+    gf, mesh = dom.globalfield, dom.mesh
+    inv = np.empty(len(gf.K_val_ids), np.int64)
+    inv[gf.K_val_ids - 1] = np.arange(1, len(inv) + 1)            # reference entry ID -> position in the canonical CSR
+    for m in range(len(dom.spec["sparse_mapping"])):
+        sid = mesh.sparse_IDs_by_el.astype(np.int64) + m * mesh.sparse_unitsize
+        assert np.array_equal(fd.get_sparse_IDs_by_el(m), inv[sid - 1])
