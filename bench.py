@@ -586,11 +586,12 @@ def main():
             case.step(False, False)
         out = {}
         for rnd in range(2):
-            for v in range(0, 20):
+            for v in range(0, 32):
                 ms, diff = C.c_double(0.0), C.c_double(0.0)
                 try:
                     fd.ctx.call("mfb_spmv_variant_bench", v, 20, C.byref(ms), C.byref(diff) if rnd == 0 else None)
-                except m.lib.MfbError:
+                except m.lib.MfbError as e:
+                    out.setdefault(v, []).append(f"error: {e}"[:120])
                     continue
                 out.setdefault(v, []).append(round(ms.value, 4))
                 if rnd == 0:

@@ -48,7 +48,8 @@ enum {
     MFB_CGS = 4,          /* cgs!,          07_CGS.jl:10-50 */
     MFB_CGS2 = 5,         /* cgs2!,         07_CGS.jl:52-105 */
     MFB_TFQMR = 6,        /* tfqmr!,        08_QMR.jl:3-76 */
-    MFB_LSQR = 7          /* lsqr!,         06_LSQR.jl:10-73 (needs A' x: transposed block SpMV) */
+    MFB_LSQR = 7,         /* lsqr!,         06_LSQR.jl:10-73 (needs A' x: transposed block SpMV) */
+    MFB_IDRS_ORIGINAL = 8 /* idrs_original!, 04_IDRs.jl:97-169 ("not used" in the reference; restated as it is, including :147) */
 };
 /* Pr_func! / Pl_func of iterative_Solve! (02_Preconditioner.jl:78-177) */
 enum { MFB_PR_JACOBI = 0 /* Pr_Jacobi! by diagonal (default) */, MFB_PR_JACOBI_COLUMN = 1 /* normalized_by_column = true */,

@@ -430,7 +430,7 @@ def update_OneStep(time_discretization, max_iter=4, fem_domain=None, log=None):
 
 
 _METHODS = {"idrs": L.MFB_IDRS, "bicgstabl_GS": L.MFB_BICGSTABL_GS, "bicgstabl": L.MFB_BICGSTABL, "gmres": L.MFB_GMRES,
-            "cgs": L.MFB_CGS, "cgs2": L.MFB_CGS2, "tfqmr": L.MFB_TFQMR, "lsqr": L.MFB_LSQR}
+            "cgs": L.MFB_CGS, "cgs2": L.MFB_CGS2, "tfqmr": L.MFB_TFQMR, "lsqr": L.MFB_LSQR, "idrs_original": L.MFB_IDRS_ORIGINAL}
 _PR = {"Pr_Jacobi": L.PR_JACOBI, "Pr_Jacobi_column": L.PR_JACOBI_COLUMN, "Identity": L.PR_IDENTITY}
 _PL = {"Identity": L.PL_IDENTITY, "Pl_Jacobi": L.PL_JACOBI, "Pl_Jacobi_row": L.PL_JACOBI_ROW}
 

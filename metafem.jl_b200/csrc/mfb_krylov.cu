@@ -794,10 +794,34 @@ __global__ void __launch_bounds__(256) k_fused(const Fused* __restrict__ Fg, con
 // five). Row boundaries inside a batch are resolved with predicated adds on the (rare) slow path; a batch that lies inside one
 // row takes the FMA fast path. With DOT the kernel also accumulates sum_rows w[row] . y[row] (the dot product the Krylov
 // method takes of the fresh product: r_shadow' A u) and finishes it in its tail: no second pass over y, no extra launch.
+// load flavours of the SpMV streams (template parameter LDK): 0 = ld.global.cs (evict-first, still allocates in L1),
+// 1 = L1::no_allocate for the value and column streams (they are read once: keep L1 for the x gathers; the L2::evict_first
+// qualifier is accepted by ptxas for 256-bit vector loads only),
+// 2 = as 1 and the x gathers marked L1::evict_last
+template <int LDK> __device__ __forceinline__ double ld_stream_f64(const double* p) {
+    if constexpr (LDK == 0) return __ldcs(p);
+    double v;
+    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+template <int LDK> __device__ __forceinline__ int ld_stream_s32(const int* p) {
+    if constexpr (LDK == 0) return __ldg(p);
+    int v;
+    asm volatile("ld.global.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+template <int LDK> __device__ __forceinline__ double ld_gather_f64(const double* p) {
+    if constexpr (LDK != 2) return __ldg(p);
+    double v;
+    asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
 // the stream loop of one warp (its RW consecutive rows)
-template <int NV, int UNR, int RW>
+template <int NV, int UNR, int RW, int LDK>
 __device__ __forceinline__ void spmv_mr_rows(const int* __restrict__ nodeptr, const int* __restrict__ nodecol, const double* __restrict__ K,
                                           const double* __restrict__ x, double* __restrict__ y, int64_t N, int64_t row0) {
+    static_assert(RW <= 31, "lane l holds the row pointer of row l: at most 31 rows per warp");
     constexpr int B = NV * NV, EPW = 32 / B, ACTIVE = EPW * B, W = UNR * EPW;
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -819,8 +843,8 @@ __device__ __forceinline__ void spmv_mr_rows(const int* __restrict__ nodeptr, co
     for (int u = 0; u < UNR; ++u) {
         a[u] = 0.0;
         const bool ok = e + u * EPW < deg;
-        v[u] = ok ? __ldcs(Kp + u * ACTIVE) : 0.0;
-        c[u] = ok ? __ldg(Cp + u * EPW) : 0;
+        v[u] = ok ? ld_stream_f64<LDK>(Kp + u * ACTIVE) : 0.0;
+        c[u] = ok ? ld_stream_s32<LDK>(Cp + u * EPW) : 0;
     }
     for (;;) {
         double vn[UNR];
@@ -830,12 +854,12 @@ __device__ __forceinline__ void spmv_mr_rows(const int* __restrict__ nodeptr, co
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {                                  // streams of the NEXT batch first ...
             const bool ok = e + W + u * EPW < deg;
-            vn[u] = ok ? __ldcs(Kp + u * ACTIVE) : 0.0;
-            cn[u] = ok ? __ldg(Cp + u * EPW) : 0;
+            vn[u] = ok ? ld_stream_f64<LDK>(Kp + u * ACTIVE) : 0.0;
+            cn[u] = ok ? ld_stream_s32<LDK>(Cp + u * EPW) : 0;
         }
         double xg[UNR];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) xg[u] = __ldg(xk + (size_t)c[u] * NV);   // ... then the dependent gathers of this one
+        for (int u = 0; u < UNR; ++u) xg[u] = ld_gather_f64<LDK>(xk + (size_t)c[u] * NV);   // ... then the dependent gathers of this one
         const int bend = base + W;
         if (bend < hi) {                                                  // the whole batch lies inside row cr
 #pragma unroll
@@ -913,20 +937,20 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
         if (spins > (1ll << 26)) __trap();                 // a copy that never lands must not hang the GPU
 }
 
-template <int NV, int UNR> struct TmaStage {
+template <int NV, int UNR, int NBATCH = 4> struct TmaStage {
     static constexpr int B = NV * NV, EPW = 32 / B, W = UNR * EPW;
-    static constexpr int NB = (W % 4 == 0) ? 4 : 4;        // batches per stage
+    static constexpr int NB = NBATCH;                      // batches per stage
     static constexpr int E = NB * W;                       // entries per stage (multiple of 4: 16-byte aligned copies)
     static constexpr int VB = E * B * 8, CB = E * 4, SB = VB + CB;
     static_assert(E % 4 == 0 && VB % 16 == 0 && CB % 16 == 0, "bulk copies need 16-byte granularity");
 };
 
-template <int NV, int UNR, int RW, int NSTG, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_spmv_tma(const int* __restrict__ nodeptr, const int* __restrict__ nodecol,
+template <int NV, int UNR, int RW, int NSTG, int WARPS, int NBATCH = 4, int MINB = 0>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k_spmv_tma(const int* __restrict__ nodeptr, const int* __restrict__ nodecol,
                                                          const double* __restrict__ K, const double* __restrict__ x,
                                                          double* __restrict__ y, int64_t N, const double* __restrict__ sc) {
     if (sc != nullptr && *reinterpret_cast<const volatile double*>(sc + SC_STOP) != 0.0) return;
-    using T = TmaStage<NV, UNR>;
+    using T = TmaStage<NV, UNR, NBATCH>;
     constexpr int B = T::B, EPW = T::EPW, ACTIVE = EPW * B, W = T::W, NB = T::NB, E = T::E, VB = T::VB, SB = T::SB;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char tma_smem[];
@@ -1046,7 +1070,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_spmv_tma(const int* __restrict__
     }
 }
 
-template <int NV, int UNR, int RW, bool DOT, int MINB = 0>
+template <int NV, int UNR, int RW, bool DOT, int MINB = 0, int LDK = 0>
 __global__ void __launch_bounds__(256, MINB) k_spmv_mr(const int* __restrict__ nodeptr, const int* __restrict__ nodecol,
                                                  const double* __restrict__ K, const double* __restrict__ x,
                                                  double* __restrict__ y, int64_t N, const double* __restrict__ wdot,
@@ -1057,7 +1081,7 @@ __global__ void __launch_bounds__(256, MINB) k_spmv_mr(const int* __restrict__ n
     double dacc = 0.0;
     const int64_t row0 = (blockIdx.x * (int64_t)8 + warp) * RW;
     if (row0 < N) {
-        spmv_mr_rows<NV, UNR, RW>(nodeptr, nodecol, K, x, y, N, row0);
+        spmv_mr_rows<NV, UNR, RW, LDK>(nodeptr, nodecol, K, x, y, N, row0);
         if constexpr (DOT) {
             // the dot product of the warp's fresh rows: the nr * NV values were written by lanes of this warp a moment ago
             __syncwarp();
@@ -1248,12 +1272,12 @@ int spmv_rw() {
     }
     return rw;
 }
-template <int NV, int RW, int NSTG, int WARPS>
+template <int NV, int RW, int NSTG, int WARPS, int NBATCH = 4, int MINB = 0>
 void launch_tma(mfb_ctx* ctx, const double* K, const double* x, double* y, const double* sc) {
     constexpr int UNR = SpmvUnroll<NV>::value;
-    using T = TmaStage<NV, UNR>;
+    using T = TmaStage<NV, UNR, NBATCH>;
     const int smem = WARPS * NSTG * T::SB + WARPS * NSTG * 8;
-    auto kern = k_spmv_tma<NV, UNR, RW, NSTG, WARPS>;
+    auto kern = k_spmv_tma<NV, UNR, RW, NSTG, WARPS, NBATCH, MINB>;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1987,6 +2011,113 @@ int bicgstabl_lu(Solver& S, double* x, const double* b, double* r, double tol, i
     }
 }
 
+// x = A \ b for a small dense system on the host: Gaussian elimination with partial pivoting (what Julia's `\` does for a square
+// matrix: lu!). A is s x s row-major and is overwritten.
+void dense_solve(std::vector<double>& Am, std::vector<double>& rhs, std::vector<double>& sol, int s) {
+    for (int c = 0; c < s; ++c) {
+        int pv = c;
+        for (int i = c + 1; i < s; ++i) if (std::fabs(Am[i * s + c]) > std::fabs(Am[pv * s + c])) pv = i;
+        if (pv != c) { for (int j = 0; j < s; ++j) std::swap(Am[c * s + j], Am[pv * s + j]); std::swap(rhs[c], rhs[pv]); }
+        for (int i = c + 1; i < s; ++i) {
+            const double f = Am[i * s + c] / Am[c * s + c];
+            for (int j = c; j < s; ++j) Am[i * s + j] -= f * Am[c * s + j];
+            rhs[i] -= f * rhs[c];
+        }
+    }
+    for (int i = s - 1; i >= 0; --i) {
+        double v = rhs[i];
+        for (int j = i + 1; j < s; ++j) v -= Am[i * s + j] * sol[j];
+        sol[i] = v / Am[i * s + i];
+    }
+}
+
+// modify_Omega (04_IDRs.jl:1-8) on the host from the three reductions |v1|^2, |v2|^2, v1'v2
+double modify_omega_host(double n1sq, double n2sq, double d) {
+    const double angle = 0.70710678118654752440;
+    const double n1 = std::sqrt(n1sq), n2 = std::sqrt(n2sq);
+    const double rho = std::fabs(d / (n1 * n2));
+    double omega = d / (n1 * n1);
+    if (rho < angle) omega = omega * angle / rho;
+    return omega;
+}
+
+// idrs_original!  (04_IDRs.jl:97-169; "not used, not exploiting orthogonality"). Restated operation by operation, INCLUDING the
+// k == 0 branch that overwrites r with Pl(A Q) instead of subtracting it (:143-148): the method is exported, so it is provided
+// with the reference's behaviour, not repaired. Vectors: P[s], U[s], G[s], Q, V, Ar. Scalars on the host (M \ f is a dense LU).
+int idrs_original(Solver& S, double* x, const double* b, double* r, double tol, int maxiter, int s, uint64_t seed, int pass,
+                  std::vector<double*>& W, int* iters) {
+    mfb_ctx* ctx = S.ctx;
+    const int64_t n = S.n;
+    Vec V_{S};
+    double res;
+    MFB_TRY(true_residual(S, r, b, x, &res));
+    if (res <= tol) { *iters = 0; return MFB_OK; }
+    int iter = 1;
+    double** P = &W[0];
+    double** U = &W[s];
+    double** G = &W[2 * s];
+    double *Q = W[3 * s], *V = W[3 * s + 1], *Ar = W[3 * s + 2];
+    for (int k = 0; k < s; ++k)
+        LAUNCH(k_rand, RED_BLOCKS, TPB, P[k], n, (unsigned long long)seed, (unsigned long long)(pass * 64 + k), ctx->gid.p, ctx->n_var);
+    std::vector<double> M(s * s, 0.0), f(s, 0.0), c(s, 0.0);
+    std::vector<const double*> xs(s + 1), ys(s + 1);
+    std::vector<double> cf(s + 1);
+    double omega = 1.0, n2 = 0.0;
+    auto fill_M_col = [&](int k) -> int {                   // M[i, k] = P[i]' G[k]
+        for (int i = 0; i < s; ++i) { xs[i] = P[i]; ys[i] = G[k]; }
+        MFB_TRY(S.dots(s, xs.data(), ys.data()));
+        for (int i = 0; i < s; ++i) M[i * s + k] = ctx->h_scal[i];
+        return MFB_OK;
+    };
+    for (int k = 0; k < s; ++k) {                           // (:113-124)
+        MFB_CUDA(cudaMemcpyAsync(U[k], r, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        MFB_TRY(S.mul(G[k], r));
+        const double* a3[3] = {G[k], r, G[k]};
+        const double* b3[3] = {G[k], r, r};
+        MFB_TRY(S.dots(3, a3, b3));
+        omega = modify_omega_host(ctx->h_scal[0], ctx->h_scal[1], ctx->h_scal[2]);
+        MFB_TRY(V_.add(x, {omega}, {U[k]}));
+        MFB_TRY(V_.add(r, {-omega}, {G[k]}, &n2));
+        MFB_TRY(fill_M_col(k));
+    }
+    while (true) {
+        if (S.nn(n2) <= tol || iter >= maxiter) { *iters = iter; return MFB_OK; }      // (:128)
+        iter++;
+        for (int k = 0; k <= s; ++k) {
+            for (int i = 0; i < s; ++i) { xs[i] = P[i]; ys[i] = r; }
+            MFB_TRY(S.dots(s, xs.data(), ys.data()));
+            for (int i = 0; i < s; ++i) f[i] = ctx->h_scal[i];
+            {
+                std::vector<double> Am(M), rhs(f);
+                dense_solve(Am, rhs, c, s);                 // c = M \ f (:135)
+            }
+            // V = r - sum c_i G[i];  Q = sum c_i U[i]   (:137-144)
+            for (int i = 0; i < s; ++i) { cf[i] = -c[i]; xs[i] = G[i]; }
+            cf[s] = 1.0; xs[s] = r;
+            MFB_TRY(S.lincomb(V, 0.0, s + 1, cf.data(), xs.data()));
+            for (int i = 0; i < s; ++i) { cf[i] = c[i]; xs[i] = U[i]; }
+            MFB_TRY(S.lincomb(Q, 0.0, s, cf.data(), xs.data()));
+            if (k == 0) {
+                MFB_TRY(S.mul(Ar, V));
+                const double* a3[3] = {Ar, V, Ar};
+                const double* b3[3] = {Ar, V, V};
+                MFB_TRY(S.dots(3, a3, b3));
+                omega = modify_omega_host(ctx->h_scal[0], ctx->h_scal[1], ctx->h_scal[2]);
+                MFB_TRY(V_.add(Q, {omega}, {V}));
+                MFB_TRY(V_.add(x, {1.0}, {Q}));
+                MFB_TRY(S.mul(r, Q));                       // r = Pl(A Q): as the reference has it (:147-148)
+                MFB_TRY(V_.dot(r, r, &n2));
+            } else {
+                MFB_TRY(V_.set(U[k - 1], {1.0, omega}, {Q, V}));
+                MFB_TRY(S.mul(G[k - 1], U[k - 1]));
+                MFB_TRY(V_.add(x, {1.0}, {U[k - 1]}));
+                MFB_TRY(V_.add(r, {-1.0}, {G[k - 1]}, &n2));
+                MFB_TRY(fill_M_col(k - 1));
+            }
+        }
+    }
+}
+
 // Hessenberg least squares by Givens rotations (05_GMRES.jl:7-37): H is (w+1) x w column-major with leading dimension ld
 void hessenberg_solve(std::vector<double>& H, int ld, int w, std::vector<double>& rhs) {
     for (int i = 0; i < w; ++i) {
@@ -2256,7 +2387,7 @@ extern "C" int mfb_krylov_solve_ex(mfb_ctx* ctx, int method, int s, int maxiter,
                                    int pr_mode, int pl_mode, int checkiter, double* delta_out, mfb_solve_info* info) {
     if (!ctx) return MFB_ERR_ARG;
     MFB_REQUIRE(ctx->U > 0 && ctx->K_total.p, MFB_ERR_STATE, "mfb_krylov_solve: pattern/matrix not built");
-    MFB_REQUIRE(method >= MFB_IDRS && method <= MFB_LSQR, MFB_ERR_ARG, "unknown Krylov method");
+    MFB_REQUIRE(method >= MFB_IDRS && method <= MFB_IDRS_ORIGINAL, MFB_ERR_ARG, "unknown Krylov method");
     MFB_REQUIRE(pr_mode >= MFB_PR_JACOBI && pr_mode <= MFB_PR_IDENTITY && pl_mode >= MFB_PL_IDENTITY && pl_mode <= MFB_PL_JACOBI_ROW,
                 MFB_ERR_ARG, "unknown preconditioner mode");
     MFB_REQUIRE(s >= 1 && (method == MFB_GMRES ? s + 1 <= MAXT : (2 * s + 2 <= MAXT && s + 2 <= MAXB && s <= MAXD)), MFB_ERR_ARG,
@@ -2278,6 +2409,7 @@ extern "C" int mfb_krylov_solve_ex(mfb_ctx* ctx, int method, int s, int maxiter,
         case MFB_CGS: nw = 5; break;
         case MFB_CGS2: case MFB_TFQMR: nw = 8; break;
         case MFB_LSQR: nw = 4; break;
+        case MFB_IDRS_ORIGINAL: nw = 3 * s + 3; break;
     }
     const int nvec = nw + 3;  // + x, r, (spare)
     MFB_TRY(ensure_work(ctx, nvec, n));
@@ -2356,6 +2488,7 @@ extern "C" int mfb_krylov_solve_ex(mfb_ctx* ctx, int method, int s, int maxiter,
             case MFB_CGS2: MFB_TRY(cgs2(S, x, b, r, ptol, maxiter, seed, pass, W, &it)); break;
             case MFB_TFQMR: MFB_TRY(tfqmr(S, x, b, r, ptol, maxiter, checkiter > 0 ? checkiter : 200, W, &it)); break;
             case MFB_LSQR: MFB_TRY(lsqr(S, x, b, r, ptol, maxiter, W, &it)); break;
+            case MFB_IDRS_ORIGINAL: MFB_TRY(idrs_original(S, x, b, r, ptol, maxiter, s, seed, pass, W, &it)); break;
         }
         inf.iterations += it;
         MFB_TRY(true_residual(S, r, b, x, &res, false));        // the plain b - A x (:45-48)
@@ -2437,10 +2570,18 @@ extern "C" int mfb_spmv_variant_bench(mfb_ctx* ctx, int variant, int reps, doubl
             case 22: launch_tma<3, 16, 3, 8>(ctx, K, x, y, nullptr); break;
             case 23: launch_tma<3, 8, 4, 4>(ctx, K, x, y, nullptr); break;
             case 24: launch_tma<3, 16, 2, 8>(ctx, K, x, y, nullptr); break;
+            case 25: launch_tma<3, 16, 2, 4, 4, 4>(ctx, K, x, y, nullptr); break;      // 4 warps, 2 stages: 36 kB per CTA, up to 4 CTAs
+            case 26: launch_tma<3, 16, 3, 4, 4, 4>(ctx, K, x, y, nullptr); break;      // 4 warps, 3 stages: 55 kB per CTA
+            // load-policy flavours of the multi-row kernel (streams not allocated in L1, evict-first in L2)
+            case 27: LAUNCH((k_spmv_mr<3, 5, 8, false, 4, 1>), g(64), 256, np, nc, K, x, y, N, (const double*)nullptr, (double*)nullptr, (double*)nullptr, (double*)nullptr, (unsigned*)nullptr, 0); break;
+            case 28: LAUNCH((k_spmv_mr<3, 5, 8, false, 4, 2>), g(64), 256, np, nc, K, x, y, N, (const double*)nullptr, (double*)nullptr, (double*)nullptr, (double*)nullptr, (unsigned*)nullptr, 0); break;
+            case 29: LAUNCH((k_spmv_mr<3, 5, 16, false, 4, 1>), g(128), 256, np, nc, K, x, y, N, (const double*)nullptr, (double*)nullptr, (double*)nullptr, (double*)nullptr, (unsigned*)nullptr, 0); break;
+            case 30: LAUNCH((k_spmv_mr<3, 5, 16, false, 4, 2>), g(128), 256, np, nc, K, x, y, N, (const double*)nullptr, (double*)nullptr, (double*)nullptr, (double*)nullptr, (unsigned*)nullptr, 0); break;
+            case 31: LAUNCH((k_spmv_mr<3, 5, 24, false, 4, 0>), g(192), 256, np, nc, K, x, y, N, (const double*)nullptr, (double*)nullptr, (double*)nullptr, (double*)nullptr, (unsigned*)nullptr, 0); break;
             default: break;
         }
     };
-    MFB_REQUIRE(variant >= 0 && variant <= 24, MFB_ERR_ARG, "unknown SpMV variant");
+    MFB_REQUIRE(variant >= 0 && variant <= 31, MFB_ERR_ARG, "unknown SpMV variant");
     for (int i = 0; i < 3; ++i) launch(variant);
     MFB_CUDA(cudaEventRecord(e0, ctx->stream));
     for (int i = 0; i < reps; ++i) launch(variant);

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmetafem_b200.so")
 
 MFB_OK, MFB_NOT_CONVERGED = 0, 1
-MFB_IDRS, MFB_BICGSTABL_GS, MFB_BICGSTABL, MFB_GMRES, MFB_CGS, MFB_CGS2, MFB_TFQMR, MFB_LSQR = range(8)
+MFB_IDRS, MFB_BICGSTABL_GS, MFB_BICGSTABL, MFB_GMRES, MFB_CGS, MFB_CGS2, MFB_TFQMR, MFB_LSQR, MFB_IDRS_ORIGINAL = range(9)
 PR_JACOBI, PR_JACOBI_COLUMN, PR_IDENTITY = 0, 1, 2
 PL_IDENTITY, PL_JACOBI, PL_JACOBI_ROW = 0, 1, 2
 VEC_X, VEC_DX, VEC_X_STAR, VEC_RESIDUE = 0, 1, 2, 3

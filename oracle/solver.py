@@ -199,6 +199,80 @@ def idrs(x, A, b, r, tol, maxiter, s=4, rng=None, Pl=Identity, **kw):    # 04_ID
         it += 1
 
 
+def fem_rand_seeded(n_nodes, nv, seed, stream_id):
+    """The library's seeded stand-in for FEM_rand (unseeded cuRAND in the reference, 04_GPU_Utils.jl:22) in REFERENCE layout:
+    entry g + v N gets the counter-based value of (seed, stream, g nv + v) -- splitmix64, see k_rand in csrc/mfb_krylov.cu.
+    Lets a test run the oracle and the CUDA path with the SAME shadow vectors."""
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+    def sm64(z):
+        with np.errstate(over="ignore"):
+            z = (z + np.uint64(0x9E3779B97F4A7C15)) & M
+            z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & M
+            z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & M
+            return z ^ (z >> np.uint64(31))
+
+    with np.errstate(over="ignore"):
+        base = sm64(np.uint64(seed) ^ (np.uint64(stream_id) * np.uint64(0xD1B54A32D192ED03) & M))
+        g = np.arange(n_nodes, dtype=np.uint64)
+        out = np.empty(n_nodes * nv)
+        for v in range(nv):
+            h = sm64((base + g * np.uint64(nv) + np.uint64(v)) & M)
+            out[v * n_nodes:(v + 1) * n_nodes] = (h >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    return out
+
+
+def idrs_original(x, A, b, r, tol, maxiter, s=4, rng=None, Pl=Identity, P=None, **kw):   # 04_IDRs.jl:97-169
+    """"not used, not exploiting orthogonality" in the reference; restated as written, including the k == 0 branch that
+    overwrites r with Pl(A Q) (:147-148)."""
+    r[:] = Pl(b - A @ x)
+    if normalized_norm(r) <= tol:
+        return 0
+    it = 1
+    n = len(b)
+    P = [rng.random(n) for _ in range(s)] if P is None else P
+    U = [np.zeros(n) for _ in range(s)]
+    G = [np.zeros(n) for _ in range(s)]
+    M = np.zeros((s, s))
+    f = np.zeros(s)
+    omega = 1.0
+    for k in range(s):
+        U[k][:] = r
+        G[k][:] = Pl(A @ r)
+        omega = modify_Omega(G[k], r)
+        x += omega * U[k]
+        r -= omega * G[k]
+        for i in range(s):
+            M[i, k] = np.dot(P[i], G[k])
+    while True:
+        if normalized_norm(r) <= tol or it >= maxiter:
+            return it
+        it += 1
+        for k in range(s + 1):
+            for i in range(s):
+                f[i] = np.dot(P[i], r)
+            c = np.linalg.solve(M, f)
+            V = c[0] * G[0]
+            Q = c[0] * U[0]
+            for i in range(1, s):
+                V += c[i] * G[i]
+                Q += c[i] * U[i]
+            V = r - V
+            if k == 0:
+                Ar = Pl(A @ V)
+                omega = modify_Omega(Ar, V)
+                Q += omega * V
+                x += Q
+                r[:] = Pl(A @ Q)
+            else:
+                U[k - 1][:] = Q + omega * V
+                G[k - 1][:] = Pl(A @ U[k - 1])
+                x += U[k - 1]
+                r -= G[k - 1]
+                for i in range(s):
+                    M[i, k - 1] = np.dot(P[i], G[k - 1])
+
+
 def bicgstabl_GS(x, A, b, r, tol, maxiter, s=2, rng=None, Pl=Identity, **kw):   # 03_BiCGstabl.jl:18-96
     r[:] = Pl(b - A @ x)
     if normalized_norm(r) <= tol:

@@ -72,3 +72,19 @@ def test_preconditioner_modes(system, pr, pl, opr, opl):
     delta = m.iterative_Solve(fd, Sv_func="bicgstabl_GS", Pr_func=pr, Pl_func=pl, maxiter=4000, max_pass=10, s=4, want_delta=True)
     odelta = osv.iterative_Solve(dom, osv.bicgstabl_GS, max_pass=10, maxiter=4000, s=4, Pr_func=opr, Pl_func=opl)
     _check(dom, fd, A, exact, delta, odelta)
+
+
+def test_idrs_original_follows_the_reference_operation_by_operation(system):
+    """idrs_original! (04_IDRs.jl:97-169) is exported but "not used": it is restated as written (including :147-148, which
+    replaces r by A Q), so the check is not convergence but that the CUDA path and the oracle produce the same iterate after
+    the same number of iterations FROM THE SAME shadow vectors (the library's seeded FEM_rand, reproduced in numpy)."""
+    import metafem_b200 as m
+    dom, fd, A, exact = system
+    gf = dom.globalfield
+    N, nv, s, seed, iters = dom.mesh.variable_size, len(dom.spec["basic_vars"]), 4, 4321, 3
+    delta = m.iterative_Solve(fd, Sv_func="idrs_original!", maxiter=iters, max_pass=1, s=s, seed=seed, want_delta=True)
+    assert fd.last_solve["iterations"] == iters
+    P = [osv.fem_rand_seeded(N, nv, seed, 1 * 64 + k) for k in range(s)]
+    odelta = osv.iterative_Solve(dom, osv.idrs_original, max_pass=1, maxiter=iters, s=s, P=P)
+    assert dom.last_solve["iters"] == [iters]
+    assert np.linalg.norm(delta - odelta) <= 1e-8 * np.linalg.norm(odelta), np.linalg.norm(delta - odelta) / np.linalg.norm(odelta)

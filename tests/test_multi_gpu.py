@@ -10,15 +10,40 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.gpu
-def test_two_rank_newton_step_matches_single_gpu(built_lib):
+def _torchrun(args, env=None, nproc=2, port=29533, timeout=900):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py")] + list(args)
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=dict(os.environ, **(env or {})))
+
+
+def _need_gpus(n):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "tests", "dist_worker.py"), "6,4,3"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs (run with gpurun --gpus {n})")
+
+
+PLANES = {"peer_memory": {}, "nccl": {"MFB_P2P": "0"}, "nccl_halo": {"MFB_P2P_HALO": "0"}}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("plane", list(PLANES))
+@pytest.mark.parametrize("case", ["neo_hookean", "thermo_elasticity", "j2", "j2_fused"])
+def test_two_rank_newton_step_matches_single_gpu(built_lib, case, plane):
+    """One full update_OneStep! on 2 ranks == the same step on one GPU, for 3- and 4-variable systems and for the J2 history
+    arrays on a partitioned mesh, over every data plane (peer-memory mailboxes + halo flags, NCCL allreduce + send/recv)."""
+    _need_gpus(2)
+    out = _torchrun([case, "6,4,3"], env=PLANES[plane], port=29533 + list(PLANES).index(plane))
     assert out.returncode == 0 and "DIST_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+    print(out.stdout[-600:])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("plane", ["peer_memory", "nccl"])
+def test_two_rank_soak_with_random_stream_delays(built_lib, plane):
+    _need_gpus(2)
+    out = _torchrun(["neo_hookean", "6,4,3", "soak"], env=PLANES[plane], port=29543)
+    assert out.returncode == 0 and "SOAK_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+    print(out.stdout[-300:])
 
 
 def test_partition_covers_mesh_and_interfaces_are_consistent():
