@@ -118,6 +118,23 @@ int mfb_mesh_build_get(mfb_ctx *ctx, int32_t *controlpoint_IDs, double *x1, doub
 int mfb_mesh_build_device_ptrs(mfb_ctx *ctx, const int32_t **controlpoint_IDs, const double **x1, const double **x2,
                                const double **x3);
 
+/* First-order geometry tables of construct_TotalMesh_3D (src/mesh/ref_geometry/002_Initialization.jl:113-217) on the device,
+ * for tets (vpb = 4) and hexes (vpb = 8); connections [vpb, n_blocks] are 1-based vertex IDs. Outputs (mfb_total_mesh_get, any
+ * pointer may be NULL; 1-based, column-major like the reference's tables):
+ *   segment_vertex_IDs [2, n_segments] (max vertex first, :144-164), block_segment_IDs [6|12, n_blocks],
+ *   face_vertex_IDs / face_segment_IDs [3|4, n_faces] (:188-213), block_face_IDs [4|6, n_blocks],
+ *   boundary_face_IDs [n_boundary_faces] ascending (get_BoundaryMesh :285-290) with the block that owns each of them and its
+ *   local face number (what mesh_Classical's facet allocation / specify_eindex computes, 3_InitializeMesh.jl:119-130,165-178).
+ * numbering: MFB_NUMBERING_SORTED -- IDs = rank of the (max, next) key, one radix sort (deterministic, locality-preserving);
+ *            MFB_NUMBERING_REFERENCE -- the reference's pass-by-pass hash-slot order, FEM_Dict (src/misc/06_GPU_Dict.jl:2-162)
+ *            reproduced with sequential insertion (one legal outcome of the reference's racing insertion; serial, for parity). */
+enum { MFB_NUMBERING_SORTED = 0, MFB_NUMBERING_REFERENCE = 1 };
+int mfb_total_mesh_build(mfb_ctx *ctx, int64_t n_vert, int vpb, int64_t n_blocks, const int32_t *connections, int numbering,
+                         int64_t *n_segments, int64_t *n_faces, int64_t *n_boundary_faces);
+int mfb_total_mesh_get(mfb_ctx *ctx, int32_t *segment_vertex_IDs, int32_t *block_segment_IDs, int32_t *face_vertex_IDs,
+                       int32_t *face_segment_IDs, int32_t *block_face_IDs, int32_t *boundary_face_IDs,
+                       int32_t *boundary_face_block, int32_t *boundary_face_eindex);
+
 /* Boundary tables (4_Update_Integrator.jl:35-75; 3_InitializeMesh.jl:119-130,165-178):
  *   bdy_ref_itp_vals       [n_qb, n_a, 2, 2, 2, n_faces]   one table per local face (eindex)
  *   bdy_itg_weights        [n_qb, n_faces]

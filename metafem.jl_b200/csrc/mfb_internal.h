@@ -241,6 +241,8 @@ void mfb_comm_free(mfb_ctx* ctx);
 
 // mfb_meshbuild.cu
 void mfb_meshbuild_free(mfb_ctx* ctx);
+// mfb_totalmesh.cu
+void mfb_totalmesh_free(mfb_ctx* ctx);
 
 // mfb_qp.cu
 int mfb_qp_lookup(mfb_ctx* ctx, const std::string& name, double** p);   // creates the array (zeroed) on first use

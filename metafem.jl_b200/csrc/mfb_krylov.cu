@@ -1267,8 +1267,8 @@ int spmv_rw() {
     static int rw = -1;
     if (rw < 0) {
         const char* e = getenv("MFB_SPMV_RW");
-        rw = e ? atoi(e) : 8;
-        if (rw != 4 && rw != 16) rw = 8;
+        rw = e ? atoi(e) : 16;                                     // 16 rows per warp measured best (profiles/spmv_experiments_r2.md)
+        if (rw != 4 && rw != 8) rw = 16;
     }
     return rw;
 }

@@ -138,3 +138,28 @@ def second_order_tables_device(ctx, coors, connections, itg_order=5):
     f_el, f_eidx, cen = np.empty(nbf.value, np.int32), np.empty(nbf.value, np.int32), np.empty((nbf.value, 3))
     ctx.call("mfb_mesh_build_get", L.ptr(cp), L.ptr(xo[0]), L.ptr(xo[1]), L.ptr(xo[2]), L.ptr(f_el), L.ptr(f_eidx), L.ptr(cen))
     return np.asfortranarray(cp.T), xo, f_el, f_eidx, cen.T
+
+
+def total_mesh_device(ctx, n_vert, connections, numbering="sorted"):
+    """construct_TotalMesh_3D's tables (002_Initialization.jl:113-217) built ON THE DEVICE by ``mfb_total_mesh_build``:
+    segment / face tables, block incidences, boundary faces with their host block and local face number.
+    numbering: "sorted" (rank of the key; deterministic) or "reference" (the reference's hash-slot order, sequential insertion).
+    Returns a dict of 1-based int32 arrays shaped like the reference's column-major tables."""
+    import ctypes as C
+    from .. import lib as L
+    conn = np.ascontiguousarray(np.asarray(connections, dtype=np.int32).T)          # [n_blocks][vpb] == column-major [vpb, n_blocks]
+    nb, vpb = conn.shape
+    ns, nf, nbf = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    mode = {"sorted": L.NUMBERING_SORTED, "reference": L.NUMBERING_REFERENCE}[numbering]
+    ctx.call("mfb_total_mesh_build", int(n_vert), vpb, nb, L.ptr(conn), mode, C.byref(ns), C.byref(nf), C.byref(nbf))
+    nsb, nfb, vpf = (6, 4, 3) if vpb == 4 else (12, 6, 4)
+    out = dict(segment_vertex_IDs=np.empty((ns.value, 2), np.int32), block_segment_IDs=np.empty((nb, nsb), np.int32),
+               face_vertex_IDs=np.empty((nf.value, vpf), np.int32), face_segment_IDs=np.empty((nf.value, vpf), np.int32),
+               block_face_IDs=np.empty((nb, nfb), np.int32), boundary_face_IDs=np.empty(nbf.value, np.int32),
+               boundary_face_block=np.empty(nbf.value, np.int32), boundary_face_eindex=np.empty(nbf.value, np.int32))
+    ctx.call("mfb_total_mesh_get", *[L.ptr(out[k]) for k in ("segment_vertex_IDs", "block_segment_IDs", "face_vertex_IDs",
+                                                            "face_segment_IDs", "block_face_IDs", "boundary_face_IDs",
+                                                            "boundary_face_block", "boundary_face_eindex")])
+    for k in ("segment_vertex_IDs", "block_segment_IDs", "face_vertex_IDs", "face_segment_IDs", "block_face_IDs"):
+        out[k] = out[k].T                                                              # the reference's [rows, n] orientation
+    return out

@@ -17,6 +17,7 @@ PR_JACOBI, PR_JACOBI_COLUMN, PR_IDENTITY = 0, 1, 2
 PL_IDENTITY, PL_JACOBI, PL_JACOBI_ROW = 0, 1, 2
 VEC_X, VEC_DX, VEC_X_STAR, VEC_RESIDUE = 0, 1, 2, 3
 MAT_K_LINEAR, MAT_K_TOTAL = 0, 1
+NUMBERING_SORTED, NUMBERING_REFERENCE = 0, 1
 
 
 class MfbError(RuntimeError):
@@ -57,6 +58,9 @@ _SIGS = {
                                               C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mfb_mesh_build_get": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "mfb_mesh_build_device_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "mfb_total_mesh_build": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, _P, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                       C.POINTER(C.c_int64)]),
+    "mfb_total_mesh_get": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mfb_facets_set": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.c_int64, _P, _P]),
     "mfb_boundary_group_set": (C.c_int, [_P, C.c_int, C.c_int64, _P]),
     "mfb_pattern_build": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
