@@ -74,8 +74,12 @@ struct BlockKernels {
 };
 
 struct BoundaryGroup {
-    DevBuf<int> elem, face;  // 0-based host element and local face of each facet of the group
+    DevBuf<int> elem, face;  // 0-based host element and local face of each facet of the group, ordered by colour
     int64_t n = 0;
+    // facets of one colour share no node through their host elements: one launch per colour makes the boundary scatter
+    // conflict-free, hence bit-reproducible
+    std::vector<int64_t> color_ptr;     // [n_colors + 1] into elem / face
+    DevBuf<int> bemap;                  // [n][n_a*n_a] ENTRY (never a side slot) of every node pair of the facet's host element
 };
 
 struct Comm;       // mfb_dist.cu
@@ -119,8 +123,24 @@ struct mfb_ctx {
     DevBuf<int> iperm;      // iperm[internal] = ref node
     DevBuf<int> nodeptr;    // [N+1] node graph CSR (internal)
     DevBuf<int> nodecol;    // [U]
-    DevBuf<int> emap;       // [n_el][n_a*n_a]
+    DevBuf<int> emap;       // [n_el][n_a*n_a] scatter target of every element node pair: an entry (< U) or a side slot (U + s)
     int64_t U = 0;          // sparse_unitsize
+    // ---- deterministic scatter (pairwise accumulators) ----
+    // An accumulator that starts at zero and receives at most TWO atomic adds holds the same bits whatever their order
+    // (a + b == b + a). The m contributions an entry receives from the domain elements are therefore dealt, by their rank in
+    // the (fixed) element order, to ceil(m/2) accumulators: ranks 0,1 -> the entry itself, ranks 2,3 -> side slot 0, ... ;
+    // a combine pass then folds the side slots into the entry in slot order. Same for the residual (per node).
+    bool deterministic = true;
+    int64_t S = 0;                  // side slots of the matrix (blocks of n_var^2 values behind the U entries)
+    DevBuf<int> slot_entry;         // [S] entry each side slot belongs to (slots of one entry are consecutive)
+    DevBuf<int> ext_entry, ext_first, ext_count;   // entries that own side slots: entry, first slot, number of slots
+    int64_t n_ext = 0;
+    DevBuf<int> rmap;               // [n_el][n_a] residual scatter target of every element node: a node (< N) or a side slot (N + s)
+    int64_t SR = 0;                 // side slots of the residual (n_var values each)
+    DevBuf<int> rext_node, rext_first, rext_count;
+    int64_t n_rext = 0;
+    DevBuf<int> lin_entries;        // unique entries the boundary-group elements touch (K_total += K_linear there), lazily built
+    int64_t n_lin_entries = -1;
     DevBuf<int> ref_pos;    // [U] position of entry inside its row, ranked by reference column id (lazy)
 
     // ---- state (internal layout) ----
@@ -206,6 +226,9 @@ int mfb_field_to_internal(mfb_ctx* ctx, const double* ref_field, double* int_fie
 int mfb_export_matrix(mfb_ctx* ctx, const double* Kint, double* Kref_dev);
 int mfb_export_pattern(mfb_ctx* ctx, int* K_I, int* K_J, int* K_J_ptr, int* K_val_ids);  // device ptrs (nullable)
 int mfb_export_sparse_ids(mfb_ctx* ctx, int block, int* out_dev);
+int mfb_entry_map(mfb_ctx* ctx, const int* item_elem, int64_t n_items, int* out);   // [n_items][n_a^2] entries of the items' elements
+int mfb_combine_matrix(mfb_ctx* ctx, double* K);      // fold the side slots of K into its entries
+int mfb_combine_residue(mfb_ctx* ctx, double* res);
 
 // ---- peer-memory mailboxes of the scalar-batch allreduce (mfb_dist.cu owns them; the reduction epilogues of mfb_krylov.cu
 // publish into / read from them) ----

@@ -105,11 +105,12 @@ struct RowKey {
     __host__ __device__ unsigned long long operator()(int64_t r) const { return ((unsigned long long)r) << 32; }
 };
 
-__global__ void k_emap(const int* conn, const int* nodeptr, const int* nodecol, int n_a, int64_t n_el, int* emap) {
+// entry of node pair p of the element item_elem[item] (binary search in the element's first node's row)
+__global__ void k_emap_items(const int* conn, const int* nodeptr, const int* nodecol, int n_a, const int* item_elem, int64_t n_items, int* out) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    int64_t total = n_el * n_a * n_a;
+    int64_t total = n_items * n_a * n_a;
     if (i >= total) return;
-    int64_t e = i / (n_a * n_a);
+    int64_t e = item_elem[i / (n_a * n_a)];
     int p = (int)(i % (n_a * n_a));
     int a = conn[e * n_a + p / n_a], b = conn[e * n_a + p % n_a];
     int lo = nodeptr[a], hi = nodeptr[a + 1] - 1;
@@ -117,7 +118,79 @@ __global__ void k_emap(const int* conn, const int* nodeptr, const int* nodecol, 
         int mid = (lo + hi) >> 1;
         if (nodecol[mid] < b) lo = mid + 1; else hi = mid;
     }
-    emap[i] = lo;
+    out[i] = lo;
+}
+
+// ---- deterministic scatter maps (see mfb_internal.h) ---------------------------------------------------------------------------
+__global__ void k_iota_u32(unsigned* p, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (unsigned)i;
+}
+__global__ void k_heads(const unsigned long long* keys, int64_t n, int* head) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+// seg_start[entry] = first sorted position of the entry (+ the sentinel seg_start[U] = n)
+__global__ void k_seg_start(const int* head, const int* entry_of, int64_t n, int* seg_start, int64_t U) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n && head[i]) seg_start[entry_of[i]] = (int)i;
+    if (i == 0) seg_start[U] = (int)n;
+}
+__global__ void k_extra(const int* seg_start, int64_t U, int deterministic, int* extra) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e < U) extra[e] = deterministic ? (seg_start[e + 1] - seg_start[e] + 1) / 2 - 1 : 0;
+}
+// target of contribution vals[i] (its rank among the contributions to the entry = i - seg_start): entry or side slot
+__global__ void k_targets(const unsigned* vals, const int* entry_of, const int* seg_start, const int* side_base, int64_t n, int64_t U,
+                          int deterministic, int* target) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int e = entry_of[i];
+    const int r = (int)i - seg_start[e];
+    target[vals[i]] = (!deterministic || r < 2) ? e : (int)(U + side_base[e] + r / 2 - 1);
+}
+__global__ void k_slot_owner(const int* extra, const int* side_base, int64_t U, int* slot_entry, int* is_ext) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= U) return;
+    for (int s = 0; s < extra[e]; ++s) slot_entry[side_base[e] + s] = (int)e;
+    is_ext[e] = extra[e] > 0 ? 1 : 0;
+}
+__global__ void k_ext_list(const int* is_ext, const int* ext_rank, const int* extra, const int* side_base, int64_t U, int* ext_entry,
+                           int* ext_first, int* ext_count) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= U || !is_ext[e]) return;
+    const int j = ext_rank[e];
+    ext_entry[j] = (int)e; ext_first[j] = side_base[e]; ext_count[j] = extra[e];
+}
+__global__ void k_keys_lo(const unsigned long long* keys, const int* head, const int* entry_of, int64_t n, int* col) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n && head[i]) col[entry_of[i]] = (int)(keys[i] & 0xffffffffull);
+}
+__global__ void k_row_counts(const unsigned long long* keys, const int* head, int64_t n, int* cnt) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n && head[i]) atomicAdd(cnt + (int)(keys[i] >> 32), 1);
+}
+__global__ void k_node_keys(const int* conn, int64_t n, unsigned long long* keys) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = (unsigned long long)(unsigned)conn[i];
+}
+// residual plan: ranks among the REFERENCED nodes -> node ids (a mesh may carry control points no element references)
+__global__ void k_rank_to_node(int* v, int64_t n, const int* node_of_rank, int64_t n_ranks, int64_t N) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int t = v[i];
+    v[i] = t < n_ranks ? node_of_rank[t] : (int)(N + (t - n_ranks));
+}
+// K[entry] += its side slots in slot order, one thread per (entry with slots, block component)
+__global__ void k_combine(const int* ext_entry, const int* ext_first, const int* ext_count, int64_t n_ext, int64_t U, int BB, double* K) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_ext * BB) return;
+    const int64_t j = t / BB;
+    const int c = (int)(t - j * BB);
+    double acc = K[(size_t)ext_entry[j] * BB + c];
+    const size_t first = (size_t)(U + ext_first[j]) * BB + c;
+    for (int s = 0; s < ext_count[j]; ++s) acc += K[first + (size_t)s * BB];
+    K[(size_t)ext_entry[j] * BB + c] = acc;
 }
 
 // layout conversions ------------------------------------------------------------------------
@@ -199,15 +272,17 @@ __global__ void k_row_of_entry(const int* nodeptr, int64_t N, int* row_of_entry)
 
 // sparse_IDs_by_el[a, b, e] (column-major, e = REFERENCE element): 1-based position, in the exported reference-layout CSR,
 // of the entry that pair (a, b) of element e feeds in variable block (i, k)
-__global__ void k_sparse_ids(const int* emap, const int* elem_rank, const int* nodeptr, const int* iperm, const int* ref_pos,
-                             const int* rowptr_ref, const int* row_of_entry, int n_a, int64_t n_el, int64_t N, int i, int ks, int* out) {
+__global__ void k_sparse_ids(const int* emap, const int* slot_entry, int64_t U, const int* elem_rank, const int* nodeptr, const int* iperm,
+                             const int* ref_pos, const int* rowptr_ref, const int* row_of_entry, int n_a, int64_t n_el, int64_t N, int i,
+                             int ks, int* out) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t per = (int64_t)n_a * n_a;
     if (t >= per * n_el) return;
     const int64_t e = t / per;
     const int p = (int)(t - e * per);
     const int a = p % n_a, b = p / n_a;                     // output index a + n_a * (b + n_a * e)
-    const int ent = emap[(int64_t)elem_rank[e] * per + a * n_a + b];
+    int ent = emap[(int64_t)elem_rank[e] * per + a * n_a + b];
+    if (ent >= U) ent = slot_entry[ent - U];              // a side slot of the deterministic scatter: the entry it is folded into
     const int row_node = row_of_entry[ent];
     const int deg = nodeptr[row_node + 1] - nodeptr[row_node];
     const int64_t row = iperm[row_node] + (int64_t)i * N;
@@ -287,33 +362,122 @@ int mfb_build_permutation(mfb_ctx* ctx, const double* x1, const double* x2, cons
     return MFB_OK;
 }
 
+namespace {
+// Sorts (key, contribution index) pairs, numbers the distinct keys (`entry_of` per sorted position, count U_out) and writes the
+// scatter target of every contribution (`target[contribution]`): the key's index, or -- deterministic mode, contribution of
+// rank >= 2 -- one of the key's side slots U_out + s. Leaves seg_start[U_out + 1], extra / side_base [U_out] for the caller.
+struct SlotPlan {
+    DevBuf<int> head, entry_of, seg_start, extra, side_base;
+    int64_t U = 0, S = 0;
+};
+int plan_slots(mfb_ctx* ctx, DevBuf<unsigned long long>& keys, int64_t total, int* target, SlotPlan& P) {
+    auto pol = thrust::cuda::par.on(ctx->stream);
+    DevBuf<unsigned> vals;
+    MFB_CUDA(vals.alloc(total));
+    LAUNCH(k_iota_u32, nblk(total), TPB, vals.p, total);
+    thrust::device_ptr<unsigned long long> kp(keys.p);
+    thrust::device_ptr<unsigned> vp(vals.p);
+    thrust::stable_sort_by_key(pol, kp, kp + total, vp);             // radix sort: contributions of one key stay in element order
+    MFB_CUDA(P.head.alloc(total)); MFB_CUDA(P.entry_of.alloc(total));
+    LAUNCH(k_heads, nblk(total), TPB, keys.p, total, P.head.p);
+    thrust::device_ptr<int> hp(P.head.p), ep(P.entry_of.p);
+    thrust::inclusive_scan(pol, hp, hp + total, ep);
+    thrust::transform(pol, ep, ep + total, ep, [] __device__(int v) { return v - 1; });
+    int last = 0;
+    MFB_CUDA(cudaMemcpyAsync(&last, P.entry_of.p + total - 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    P.U = (int64_t)last + 1;
+    MFB_CUDA(P.seg_start.alloc(P.U + 1)); MFB_CUDA(P.extra.alloc(P.U)); MFB_CUDA(P.side_base.alloc(P.U));
+    LAUNCH(k_seg_start, nblk(total), TPB, P.head.p, P.entry_of.p, total, P.seg_start.p, P.U);
+    LAUNCH(k_extra, nblk(P.U), TPB, P.seg_start.p, P.U, ctx->deterministic ? 1 : 0, P.extra.p);
+    thrust::device_ptr<int> xp(P.extra.p), bp(P.side_base.p);
+    thrust::exclusive_scan(pol, xp, xp + P.U, bp);
+    int lb = 0, lx = 0;
+    MFB_CUDA(cudaMemcpyAsync(&lb, P.side_base.p + P.U - 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MFB_CUDA(cudaMemcpyAsync(&lx, P.extra.p + P.U - 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    P.S = (int64_t)lb + lx;
+    LAUNCH(k_targets, nblk(total), TPB, vals.p, P.entry_of.p, P.seg_start.p, P.side_base.p, total, P.U, ctx->deterministic ? 1 : 0, target);
+    MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MFB_OK;
+}
+int ext_lists(mfb_ctx* ctx, SlotPlan& P, DevBuf<int>* slot_entry, DevBuf<int>& ext_entry, DevBuf<int>& ext_first, DevBuf<int>& ext_count,
+              int64_t* n_ext) {
+    auto pol = thrust::cuda::par.on(ctx->stream);
+    DevBuf<int> is_ext, ext_rank, owner_tmp;
+    MFB_CUDA(is_ext.alloc(P.U)); MFB_CUDA(ext_rank.alloc(P.U));
+    DevBuf<int>& owner = slot_entry ? *slot_entry : owner_tmp;
+    MFB_CUDA(owner.alloc(P.S > 0 ? P.S : 1));
+    LAUNCH(k_slot_owner, nblk(P.U), TPB, P.extra.p, P.side_base.p, P.U, owner.p, is_ext.p);
+    thrust::device_ptr<int> ip(is_ext.p), rp(ext_rank.p);
+    thrust::exclusive_scan(pol, ip, ip + P.U, rp);
+    int lr = 0, lf = 0;
+    MFB_CUDA(cudaMemcpyAsync(&lr, ext_rank.p + P.U - 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MFB_CUDA(cudaMemcpyAsync(&lf, is_ext.p + P.U - 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_ext = (int64_t)lr + lf;
+    const int64_t na = *n_ext > 0 ? *n_ext : 1;
+    MFB_CUDA(ext_entry.alloc(na)); MFB_CUDA(ext_first.alloc(na)); MFB_CUDA(ext_count.alloc(na));
+    LAUNCH(k_ext_list, nblk(P.U), TPB, is_ext.p, ext_rank.p, P.extra.p, P.side_base.p, P.U, ext_entry.p, ext_first.p, ext_count.p);
+    MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MFB_OK;
+}
+}  // namespace
+
 int mfb_build_pattern(mfb_ctx* ctx) {
     const int64_t N = ctx->N;
     const int n_a = ctx->n_a;
     const int64_t total = ctx->n_el * n_a * n_a;
+    MFB_REQUIRE(total < 4294967295LL, MFB_ERR_ARG, "more than 2^32 element node pairs");
+    {
+        const char* e = getenv("MFB_DETERMINISTIC");
+        ctx->deterministic = !(e && e[0] == '0');
+    }
     auto pol = thrust::cuda::par.on(ctx->stream);
-    DevBuf<unsigned long long> keys;
-    MFB_CUDA(keys.alloc(total));
-    LAUNCH(k_pair_keys, nblk(total), TPB, ctx->conn.p, n_a, ctx->n_el, keys.p);
-    thrust::device_ptr<unsigned long long> kp(keys.p);
-    thrust::sort(pol, kp, kp + total);
-    auto end = thrust::unique(pol, kp, kp + total);
-    MFB_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->U = end - kp;
-    MFB_REQUIRE(ctx->U < (int64_t)2147483647, MFB_ERR_ARG, "node graph exceeds int32 indexing");
-    MFB_CUDA(ctx->nodecol.alloc(ctx->U + MFB_STREAM_PAD));
-    MFB_CUDA(cudaMemsetAsync(ctx->nodecol.p + ctx->U, 0, MFB_STREAM_PAD * sizeof(int), ctx->stream));
-    MFB_CUDA(ctx->nodeptr.alloc(N + 1));
-    LAUNCH(k_split, nblk(ctx->U), TPB, keys.p, ctx->U, ctx->nodecol.p);
-    thrust::counting_iterator<int64_t> c0(0);
-    auto rows = thrust::make_transform_iterator(c0, RowKey());
-    thrust::lower_bound(pol, kp, kp + ctx->U, rows, rows + (N + 1), thrust::device_ptr<int>(ctx->nodeptr.p));
-    MFB_CUDA(cudaStreamSynchronize(ctx->stream));
-    keys.release();
-    MFB_CUDA(ctx->emap.alloc(total));
-    LAUNCH(k_emap, nblk(total), TPB, ctx->conn.p, ctx->nodeptr.p, ctx->nodecol.p, n_a, ctx->n_el, ctx->emap.p);
+    // ---- node graph + scatter map of the matrix ----
+    {
+        DevBuf<unsigned long long> keys;
+        MFB_CUDA(keys.alloc(total));
+        LAUNCH(k_pair_keys, nblk(total), TPB, ctx->conn.p, n_a, ctx->n_el, keys.p);
+        MFB_CUDA(ctx->emap.alloc(total));
+        SlotPlan P;
+        MFB_TRY(plan_slots(ctx, keys, total, ctx->emap.p, P));
+        ctx->U = P.U;
+        ctx->S = P.S;
+        MFB_REQUIRE(ctx->U + ctx->S < (int64_t)2147483647, MFB_ERR_ARG, "node graph exceeds int32 indexing");
+        MFB_CUDA(ctx->nodecol.alloc(ctx->U + MFB_STREAM_PAD));
+        MFB_CUDA(cudaMemsetAsync(ctx->nodecol.p + ctx->U, 0, MFB_STREAM_PAD * sizeof(int), ctx->stream));
+        MFB_CUDA(ctx->nodeptr.alloc(N + 1));
+        LAUNCH(k_keys_lo, nblk(total), TPB, keys.p, P.head.p, P.entry_of.p, total, ctx->nodecol.p);
+        // row pointer: entries per row (keys are sorted by row, then column), exclusive scan
+        MFB_CUDA(cudaMemsetAsync(ctx->nodeptr.p, 0, (N + 1) * sizeof(int), ctx->stream));
+        LAUNCH(k_row_counts, nblk(total), TPB, keys.p, P.head.p, total, ctx->nodeptr.p);
+        thrust::device_ptr<int> np(ctx->nodeptr.p);
+        thrust::exclusive_scan(pol, np, np + (N + 1), np);
+        MFB_TRY(ext_lists(ctx, P, &ctx->slot_entry, ctx->ext_entry, ctx->ext_first, ctx->ext_count, &ctx->n_ext));
+    }
+    // ---- scatter map of the residual ----
+    {
+        const int64_t nconn = ctx->n_el * n_a;
+        DevBuf<unsigned long long> keys;
+        MFB_CUDA(keys.alloc(nconn));
+        LAUNCH(k_node_keys, nblk(nconn), TPB, ctx->conn.p, nconn, keys.p);
+        MFB_CUDA(ctx->rmap.alloc(nconn));
+        SlotPlan P;
+        MFB_TRY(plan_slots(ctx, keys, nconn, ctx->rmap.p, P));
+        ctx->SR = P.S;
+        MFB_TRY(ext_lists(ctx, P, nullptr, ctx->rext_node, ctx->rext_first, ctx->rext_count, &ctx->n_rext));
+        // the plan numbers the REFERENCED nodes (a mesh may carry control points no element touches): back to node ids
+        DevBuf<int> node_of_rank;
+        MFB_CUDA(node_of_rank.alloc(P.U));
+        LAUNCH(k_keys_lo, nblk(nconn), TPB, keys.p, P.head.p, P.entry_of.p, nconn, node_of_rank.p);
+        LAUNCH(k_rank_to_node, nblk(nconn), TPB, ctx->rmap.p, nconn, node_of_rank.p, P.U, N);
+        if (ctx->n_rext > 0) LAUNCH(k_rank_to_node, nblk(ctx->n_rext), TPB, ctx->rext_node.p, ctx->n_rext, node_of_rank.p, P.U, N);
+        MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     MFB_CUDA(cudaGetLastError());
     ctx->ref_pos.release();
+    ctx->n_lin_entries = -1;
     if (const char* dump = getenv("MFB_DUMP_PATTERN")) {   // experiments (profiles/exp): int64 N, int64 U, nodeptr, nodecol
         std::vector<int> hp(N + 1), hc(ctx->U);
         MFB_CUDA(cudaMemcpy(hp.data(), ctx->nodeptr.p, (N + 1) * sizeof(int), cudaMemcpyDeviceToHost));
@@ -326,6 +490,28 @@ int mfb_build_pattern(mfb_ctx* ctx) {
             fclose(f);
         }
     }
+    return MFB_OK;
+}
+
+// entries (never side slots) of all node pairs of the given elements: the scatter map of the boundary kernels
+int mfb_entry_map(mfb_ctx* ctx, const int* item_elem, int64_t n_items, int* out) {
+    LAUNCH(k_emap_items, nblk(n_items * ctx->n_a * ctx->n_a), TPB, ctx->conn.p, ctx->nodeptr.p, ctx->nodecol.p, ctx->n_a, item_elem, n_items, out);
+    MFB_CUDA(cudaGetLastError());
+    return MFB_OK;
+}
+
+int mfb_combine_matrix(mfb_ctx* ctx, double* K) {
+    if (ctx->n_ext <= 0) return MFB_OK;
+    const int BB = ctx->n_var * ctx->n_var;
+    LAUNCH(k_combine, nblk(ctx->n_ext * BB), TPB, ctx->ext_entry.p, ctx->ext_first.p, ctx->ext_count.p, ctx->n_ext, ctx->U, BB, K);
+    MFB_CUDA(cudaGetLastError());
+    return MFB_OK;
+}
+int mfb_combine_residue(mfb_ctx* ctx, double* res) {
+    if (ctx->n_rext <= 0) return MFB_OK;
+    LAUNCH(k_combine, nblk(ctx->n_rext * ctx->n_var), TPB, ctx->rext_node.p, ctx->rext_first.p, ctx->rext_count.p, ctx->n_rext, ctx->N,
+           ctx->n_var, res);
+    MFB_CUDA(cudaGetLastError());
     return MFB_OK;
 }
 
@@ -419,7 +605,7 @@ int mfb_export_sparse_ids(mfb_ctx* ctx, int block, int* out_dev) {
     int ks = 0;
     for (int kk = 0; kk < k; ++kk) ks += ctx->block_of[i * nv + kk] >= 0;
     const int64_t total = ctx->n_el * ctx->n_a * ctx->n_a;
-    LAUNCH(k_sparse_ids, nblk(total), TPB, ctx->emap.p, ctx->elem_rank.p, ctx->nodeptr.p, ctx->iperm.p, ctx->ref_pos.p, R.rowptr.p,
+    LAUNCH(k_sparse_ids, nblk(total), TPB, ctx->emap.p, ctx->slot_entry.p, ctx->U, ctx->elem_rank.p, ctx->nodeptr.p, ctx->iperm.p, ctx->ref_pos.p, R.rowptr.p,
            R.row_of_entry.p, ctx->n_a, ctx->n_el, ctx->N, i, ks, out_dev);
     MFB_CUDA(cudaStreamSynchronize(ctx->stream));
     return MFB_OK;

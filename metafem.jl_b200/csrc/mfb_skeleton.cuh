@@ -16,7 +16,8 @@
 //   conn   [n_el][NA]      int32  internal node id of local node a
 //   xyz    [N][3]          double node coordinates (AoS, one 24 B gather per node)
 //   u      [L+1][N][NV]    double x_star, node-major interleaved (one contiguous NV-gather per node)
-//   emap   [n_el][NA*NA]   int32  index of node pair (a,b) in the node-graph CSR
+//   emap   [n_el][NA*NA]   int32  scatter target of node pair (a,b): its entry in the node-graph CSR, or one of the entry's side
+//                                 slots U + s (deterministic scatter: every accumulator receives at most two atomic adds)
 //   Kval   [U][NV*NV]      double block values, row-major inside the block (BSR with NV x NV blocks)
 //   res    [N][NV]         double residual
 //   cpv[i] [N]             double CONTROLPOINT_VAR fields
@@ -35,7 +36,9 @@ struct MfbArgs {
     // mesh
     const int* conn;
     const double* xyz;
-    const int* emap;
+    const int* emap;            // scatter targets of the items' node pairs: [n_el][NA*NA] (domain: entries or side slots of the
+                                // deterministic scatter) or [n_items][NA*NA] (boundary group: entries of the facet's host element)
+    const int* rmap;            // residual scatter targets [n_el][NA]: nodes or residual side slots (boundary: conn itself)
     long long n_items;          // elements (domain) or facets of the group (boundary)
     long long N;                // nodes
     // boundary: facet -> host element / local face; domain: nullptr
@@ -200,6 +203,7 @@ struct Smem {
     double ue[F::L1][F::NA][F::NV];
     double ce[F::NC > 0 ? F::NC : 1][F::NA];
     int node[F::NA];
+    int rnode[F::NA];                              // residual scatter target of every local node
 };
 
 template <class F>
@@ -227,6 +231,7 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
         for (int a = tid; a < NA; a += TPB) {
             int g = A.conn[e * NA + a];
             S.node[a] = g;
+            S.rnode[a] = A.rmap[e * NA + a];
             S.xe[a][0] = A.xyz[3 * (size_t)g + 0];
             S.xe[a][1] = A.xyz[3 * (size_t)g + 1];
             S.xe[a][2] = A.xyz[3 * (size_t)g + 2];
@@ -245,7 +250,7 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
         constexpr int NEM = F::HAS_K ? (NA * NA + TPB - 1) / TPB : 1;
         int emr[NEM];                                   // scatter map of this element: in flight during phase B
         if constexpr (F::HAS_K) {
-            const int* em = A.emap + e * (NA * NA);
+            const int* em = A.emap + (F::BOUNDARY ? item : e) * (NA * NA);
 #pragma unroll
             for (int k = 0; k < NEM; ++k) emr[k] = tid + k * TPB < NA * NA ? em[tid + k * TPB] : 0;
         }
@@ -440,7 +445,7 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
                         }
                     }
                 }
-                if (F::HAS_RES && cgi == 0 && racc != 0.0) red_add(A.res + (size_t)S.node[a] * NV + dp, racc);
+                if (F::HAS_RES && cgi == 0 && racc != 0.0) red_add(A.res + (size_t)S.rnode[a] * NV + dp, racc);
             }
             __syncthreads();        // every warp is done with G, D and R: their storage becomes Ke
             // ---- phase D: stage the element matrix, then scatter with node-pair blocks on adjacent lanes ----
@@ -477,7 +482,7 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
 #pragma unroll
                     for (int k = 0; k < NGS; ++k) s += S.gd.G[q][k][a] * S.gu[q][v * 4 + F::gslot_id(k)];
                 }
-                if (s != 0.0) red_add(A.res + (size_t)S.node[a] * NV + v, s);
+                if (s != 0.0) red_add(A.res + (size_t)S.rnode[a] * NV + v, s);
             }
         }
     }

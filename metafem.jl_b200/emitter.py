@@ -164,7 +164,7 @@ def _form(name, spec, blk, n_a, n_q, linear, evalk=False):
     nvl = (0 if linear else L1 * nv) + len(fields)
     geo = _align16(max(8 * n_q * (9 + 1 + 3), 4 * n_a * n_a if terms else 4))
     smem = _align16(_align16(max(gd, ke)) + geo + 8 * (n_q * 4 * max(nvl, 1) + n_a * 3 + L1 * n_a * nv
-                                                      + max(len(fields), 1) * n_a) + 4 * n_a)
+                                                      + max(len(fields), 1) * n_a) + 8 * n_a)
     body = "\n".join(lines).replace("@SMEM@", str(smem))
     return body, fields, globs, smem, bool(terms), tpb, qp_in_names, qp_out_names
 

@@ -50,7 +50,9 @@ def main():
         state["sl1"] = np.full(N, 120.0)
     if case == "neo_hookean":
         state["Pl1"] = np.full(N, 0.05)
-    tol = {"neo_hookean": 1e-9, "thermo_elasticity": 1e-6, "j2": 1e-3, "j2_fused": 1e-3}[case]
+    # (the J2 script's 1e-3 is an ABSOLUTE residual tolerance: two correct solves then differ by 1e-4..1e-3 in x, which says nothing;
+    # the comparison runs at 1e-8 so that a wrong interface term would show)
+    tol = {"neo_hookean": 1e-9, "thermo_elasticity": 1e-6, "j2": 1e-8, "j2_fused": 1e-8}[case]
     s = 4 if case == "neo_hookean" else 8
     basic = spec["basic_vars"]
 

@@ -148,3 +148,32 @@ def test_sparse_ids_by_el_match_the_oracle(pair):
     for m in range(len(dom.spec["sparse_mapping"])):
         sid = mesh.sparse_IDs_by_el.astype(np.int64) + m * mesh.sparse_unitsize
         assert np.array_equal(fd.get_sparse_IDs_by_el(m), inv[sid - 1])
+
+
+def test_assembly_is_bit_reproducible(pair):
+    """Deterministic scatter (pairwise accumulators + fixed-order fold, coloured boundary launches): assembling the same state
+    twice gives the same bits in K_linear, K_total and the residual -- the reference's atomics do not (06_FEM_Kernel.jl:10,36,74)."""
+    import metafem_b200 as m
+    dom, fd = pair
+    _assemble_both(dom, fd)
+    first = [fd.get_matrix(m.lib.MAT_K_LINEAR), fd.get_matrix(m.lib.MAT_K_TOTAL), fd.get_vector(m.lib.VEC_RESIDUE)]
+    for _ in range(3):
+        td = fd.time_discretization
+        fd.K_linear_func(td, fem_domain=fd)
+        fd.K_nonlinear_func(td, fem_domain=fd)
+        again = [fd.get_matrix(m.lib.MAT_K_LINEAR), fd.get_matrix(m.lib.MAT_K_TOTAL), fd.get_vector(m.lib.VEC_RESIDUE)]
+        for a, b in zip(first, again):
+            assert np.array_equal(a, b)
+
+
+def test_solve_is_bit_reproducible(pair):
+    """... and with fixed-order reductions in the Krylov kernels the whole solve repeats: same iteration count, same bits."""
+    import metafem_b200 as m
+    dom, fd = pair
+    _assemble_both(dom, fd)
+    name, s = ("idrs", 8) if dom.spec["basic_vars"] == ["T"] else ("bicgstabl_GS", 4)
+    runs = []
+    for _ in range(2):
+        d = m.iterative_Solve(fd, Sv_func=name, maxiter=3000, max_pass=10, s=s, seed=99, want_delta=True)
+        runs.append((fd.last_solve["iterations"], d.copy()))
+    assert runs[0][0] == runs[1][0] and np.array_equal(runs[0][1], runs[1][1])
