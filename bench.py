@@ -303,7 +303,7 @@ class Case:
         self.n_nodes_global = gt.variable_size
         self.n_el_global = gt.controlpoint_IDs.shape[1]
         gx = gt.x
-        scale = 1.0 if name == "neo_hookean" else (4e-4 / 0.02 * 4.0 if name.startswith("j2") else 0.05)
+        scale = 1.0 if name in ("neo_hookean", "linear_elasticity") else (4e-4 / 0.02 * 4.0 if name.startswith("j2") else 0.05)
         gstate = [v * scale for v in initial_state(gx, 1.0 / n)]
         if self.world > 1:
             from metafem_jl_b200.frontend import partition as pt
@@ -417,6 +417,21 @@ class Case:
         if self.world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
+
+    def ilu_solve(self):
+        """The same linear system (matrix and residual of the last step) solved with the script's bicgstabl_GS! + Pl_ILU: what the
+        incomplete factorisation does to the iteration count and to the solve time (extra, not the headline)."""
+        L, s = self.env.L, WORKLOADS[self.name]["solver"]
+        defect, levels = C.c_double(0.0), C.c_int32(0)
+        self.fd.ctx.call("mfb_ilu_selftest", C.byref(defect), C.byref(levels), None, 0)
+        info = L.SolveInfo()
+        ms = self.time_call(lambda: self.fd.ctx.call("mfb_krylov_solve_ex", L.MFB_BICGSTABL_GS, s["s"], s["maxiter"], s["max_pass"],
+                                                     WORKLOADS[self.name]["tol"], 1234, L.PR_JACOBI, L.PL_ILU, 200, None, C.byref(info)))
+        return {"solver": f"bicgstabl_GS s={s['s']}, right Jacobi + left Pl_ILU (block ILU(0), hash elimination order)",
+                "solve_ms": ms, "krylov_iterations": int(info.iterations), "spmv_count": int(info.spmv_count), "passes": int(info.passes),
+                "converged": bool(info.converged), "final_residual": info.residual, "dependency_levels": int(levels.value),
+                "factorisation_defect_rel": defect.value,
+                "note": "solve_ms includes the factorisation; every product is followed by 2 x dependency_levels sweep launches"}
 
     def profile(self, level):
         self.fd.ctx.call("mfb_profile_enable", level)
@@ -628,6 +643,13 @@ def main():
     dc = None
     if world > 1 and not args.no_dist_check and not args.ncu and name == "neo_hookean":
         dc = dist_check(env, case, args)
+    ilu = None
+    if world == 1 and not args.no_extras and not args.ncu:
+        try:
+            ilu = case.ilu_solve()
+            ilu["jacobi_only"] = {"solve_ms": r["solve_ms"], "krylov_iterations": r["krylov_iterations"]["mean"]}
+        except Exception as e:
+            ilu = {"failed": f"{type(e).__name__}: {e}"}
     peak, peak_kind = hbm_peak()
     out = None
     if rank == 0:
@@ -717,6 +739,8 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+    if ilu is not None:
+        extras["neo_hookean_pl_ilu"] = ilu
     out["extra"] = extras
     if not args.no_cpu_baseline and world == 1 and name == "neo_hookean":      # the CPU port is timed beside the single-GPU run only
         try:

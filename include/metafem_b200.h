@@ -54,7 +54,10 @@ enum {
 /* Pr_func! / Pl_func of iterative_Solve! (02_Preconditioner.jl:78-177) */
 enum { MFB_PR_JACOBI = 0 /* Pr_Jacobi! by diagonal (default) */, MFB_PR_JACOBI_COLUMN = 1 /* normalized_by_column = true */,
        MFB_PR_IDENTITY = 2 };
-enum { MFB_PL_IDENTITY = 0 /* default */, MFB_PL_JACOBI = 1 /* Pl_Jacobi by diagonal */, MFB_PL_JACOBI_ROW = 2 /* normalized_by_row */ };
+enum { MFB_PL_IDENTITY = 0 /* default */, MFB_PL_JACOBI = 1 /* Pl_Jacobi by diagonal */, MFB_PL_JACOBI_ROW = 2 /* normalized_by_row */,
+       MFB_PL_ILU = 3 /* Pl_ILU (:179-194): zero-fill block ILU of the right-scaled matrix, level-scheduled sweeps; elimination order
+                         chosen for parallelism (hash ranking) where cuSPARSE ilu02! follows the row order -- same incomplete
+                         factorisation property, solutions agree at solver tolerance */ };
 
 /* vectors of GlobalField (src/solver/01_Types.jl:110-132) */
 enum { MFB_VEC_X = 0, MFB_VEC_DX = 1, MFB_VEC_X_STAR = 2, MFB_VEC_RESIDUE = 3 };
@@ -282,6 +285,11 @@ int mfb_krylov_solve(mfb_ctx *ctx, int method, int s, int maxiter, int max_pass,
  * Pl_ILU: see MFB_PL_ILU. */
 int mfb_krylov_solve_ex(mfb_ctx *ctx, int method, int s, int maxiter, int max_pass, double tol, uint64_t seed,
                         int pr_mode, int pl_mode, int checkiter, double *delta_out, mfb_solve_info *info);
+
+/* Test / diagnosis of the ILU: factorises K_total as it stands and returns max |(L U - A)_ij| over the sparsity pattern relative to
+ * max |A_ij| (zero for an exact incomplete factorisation up to rounding), the number of dependency levels of the elimination order,
+ * and applies U^-1 L^-1 to v_inout (reference layout, n = n_var*N; may be NULL). */
+int mfb_ilu_selftest(mfb_ctx *ctx, double *rel_defect, int32_t *n_levels, double *v_inout, int64_t n);
 
 /* ---- time stepping (src/solver/04_Time_Domain.jl) ----------------------------------------
  * Device-resident versions of initialize_dx! (:20-30), update_x_star! (:41-49),

@@ -432,7 +432,7 @@ def update_OneStep(time_discretization, max_iter=4, fem_domain=None, log=None):
 _METHODS = {"idrs": L.MFB_IDRS, "bicgstabl_GS": L.MFB_BICGSTABL_GS, "bicgstabl": L.MFB_BICGSTABL, "gmres": L.MFB_GMRES,
             "cgs": L.MFB_CGS, "cgs2": L.MFB_CGS2, "tfqmr": L.MFB_TFQMR, "lsqr": L.MFB_LSQR, "idrs_original": L.MFB_IDRS_ORIGINAL}
 _PR = {"Pr_Jacobi": L.PR_JACOBI, "Pr_Jacobi_column": L.PR_JACOBI_COLUMN, "Identity": L.PR_IDENTITY}
-_PL = {"Identity": L.PL_IDENTITY, "Pl_Jacobi": L.PL_JACOBI, "Pl_Jacobi_row": L.PL_JACOBI_ROW}
+_PL = {"Identity": L.PL_IDENTITY, "Pl_Jacobi": L.PL_JACOBI, "Pl_Jacobi_row": L.PL_JACOBI_ROW, "Pl_ILU": L.PL_ILU}
 
 
 def iterative_Solve(fem_domain, Sv_func="idrs", Pr_func="Pr_Jacobi", Pl_func="Identity", max_pass=4, maxiter=2000, s=4,
@@ -440,7 +440,7 @@ def iterative_Solve(fem_domain, Sv_func="idrs", Pr_func="Pr_Jacobi", Pl_func="Id
     """iterative_Solve!(globalfield; Sv_func!, Pr_func!, Pl_func, max_pass, maxiter, s) (02_Preconditioner.jl:32-76).
     Sv_func: idrs, bicgstabl_GS, bicgstabl, gmres, cgs, cgs2, tfqmr, lsqr (a trailing "!" is accepted);
     Pr_func: Pr_Jacobi (default) | Pr_Jacobi_column (normalized_by_column = true) | Identity;
-    Pl_func: Identity (default) | Pl_Jacobi | Pl_Jacobi_row (normalized_by_row = true). Pl_ILU is not provided."""
+    Pl_func: Identity (default) | Pl_Jacobi | Pl_Jacobi_row (normalized_by_row = true) | Pl_ILU."""
     name = Sv_func.rstrip("!")
     if name not in _METHODS:
         raise ValueError(f"Sv_func {Sv_func!r} is not provided (supported: {', '.join(_METHODS)})")

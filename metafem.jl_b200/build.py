@@ -5,7 +5,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmetafem_b200.so")
-SOURCES = ["mfb_api.cu", "mfb_pattern.cu", "mfb_krylov.cu", "mfb_dist.cu", "mfb_qp.cu", "mfb_vtk.cpp", "mfb_meshbuild.cu", "mfb_totalmesh.cu"]
+SOURCES = ["mfb_api.cu", "mfb_pattern.cu", "mfb_krylov.cu", "mfb_dist.cu", "mfb_qp.cu", "mfb_vtk.cpp", "mfb_meshbuild.cu", "mfb_totalmesh.cu", "mfb_ilu.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "--extended-lambda"]
 

@@ -266,6 +266,10 @@ void mfb_comm_free(mfb_ctx* ctx);
 void mfb_meshbuild_free(mfb_ctx* ctx);
 // mfb_totalmesh.cu
 void mfb_totalmesh_free(mfb_ctx* ctx);
+// mfb_ilu.cu
+int mfb_ilu_factor(mfb_ctx* ctx, const double* A, int* n_levels);   // A: [U][n_var^2] block values (internal layout)
+int mfb_ilu_apply(mfb_ctx* ctx, double* v);                         // v <- U^-1 L^-1 v, internal layout
+void mfb_ilu_free(mfb_ctx* ctx);
 
 // mfb_qp.cu
 int mfb_qp_lookup(mfb_ctx* ctx, const std::string& name, double** p);   // creates the array (zeroed) on first use

@@ -1361,10 +1361,13 @@ struct Solver {
     int spmv = 0;
 
     const double* pl = nullptr;   // Pl_Jacobi vector (left preconditioner: b ./= jac_vec after every product), or null
+    bool pl_ilu = false;          // Pl_ILU: b <- U^-1 L^-1 b after every product (mfb_ilu.cu)
+    bool has_pl() const { return pl != nullptr || pl_ilu; }
 
     const unsigned char* mask() const { return mfb_is_distributed(ctx) ? ctx->owned.p : nullptr; }
     int Pl(double* v) {
         if (pl) LAUNCH(k_div_inplace, nblk(n), TPB, v, pl, n);
+        if (pl_ilu) MFB_TRY(mfb_ilu_apply(ctx, v));
         return MFB_OK;
     }
     // y = Pl(A x): every mul! of the reference's solvers is followed by Pl(.)
@@ -1531,7 +1534,7 @@ struct Solver {
     // register cap -- 3.3 ms instead of 2.2 ms per SpMV measured; MFB_SPMV_DOT=1 re-enables it for experiments)
     bool can_fuse_spmv_dot() const {
         static const bool want = [] { const char* e = getenv("MFB_SPMV_DOT"); return e && e[0] == '1'; }();
-        return want && mfb_spmv_kind(ctx) == 1 && ctx->n_var <= 5 && !pl && !mfb_is_distributed(ctx);
+        return want && mfb_spmv_kind(ctx) == 1 && ctx->n_var <= 5 && !has_pl() && !mfb_is_distributed(ctx);
     }
     int mul_dot(double* y, const double* x, const double* w, const ScOp& op, int dot_prog) {
         spmv++;
@@ -1577,14 +1580,15 @@ struct FB {
 int true_residual(Solver& S, double* r, const double* b, const double* x, double* res, bool left = true) {
     mfb_ctx* ctx = S.ctx;
     const double* keep = S.pl;
-    S.pl = nullptr;
+    const bool keep_ilu = S.pl_ilu;
+    S.pl = nullptr; S.pl_ilu = false;
     int rc = S.mul(r, x);
-    S.pl = keep;
+    S.pl = keep; S.pl_ilu = keep_ilu;
     MFB_TRY(rc);
     double c[1] = {1.0};
     const double* xs[1] = {b};
     double n2;
-    if (left && S.pl) {
+    if (left && S.has_pl()) {
         MFB_TRY(S.lincomb(r, -1.0, 1, c, xs));
         MFB_TRY(S.Pl(r));
         double d;
@@ -1860,7 +1864,24 @@ int bicgstabl_gs(Solver& S, double* x, const double* b, double* r, double tol, i
     double* hslot = ctx->h_scal + 32;                 // two read-back slots of 8 doubles: sc[0..8)
     MFB_TRY(S.run(p_rho0));
     const ScOp none{OP_NONE, 0, 0, 0};
+    // the launches of an outer iteration that was enqueued after the stop flag went up do nothing: their profile events and
+    // SpMV counts are dropped again (marks of the last two iterations)
+    struct Mark { size_t ev[MFB_T_COUNT][2]; int spmv; int64_t launches; } marks[2];
+    auto take_mark = [&](Mark& m) {
+        for (int q = 0; q < MFB_T_COUNT; ++q) { m.ev[q][0] = ctx->prof[q].start.size(); m.ev[q][1] = ctx->prof[q].stop.size(); }
+        m.spmv = S.spmv; m.launches = ctx->launches;
+    };
+    auto drop_after = [&](const Mark& m) {
+        for (int q = 0; q < MFB_T_COUNT; ++q) {
+            ProfEvents& P = ctx->prof[q];
+            if (q == MFB_T_SOLVE) continue;                         // the enclosing solve scope is still open
+            while (P.start.size() > m.ev[q][0]) { ctx->event_pool.push_back(P.start.back()); P.start.pop_back(); }
+            while (P.stop.size() > m.ev[q][1]) { ctx->event_pool.push_back(P.stop.back()); P.stop.pop_back(); }
+        }
+        S.spmv = m.spmv; ctx->launches = m.launches;
+    };
     for (int k = 0;; ++k) {
+        take_mark(marks[k & 1]);
         for (int j = 0; j < s; ++j) {
             MFB_TRY(S.run(pa[j]));
             MFB_TRY(S.mul_dot(U[j + 1], U[j], r_shadow, ScOp{OP_ALPHA, 0, 0, 0}, pdotU[j]));
@@ -1874,7 +1895,11 @@ int bicgstabl_gs(Solver& S, double* x, const double* b, double* r, double tol, i
         MFB_CUDA(cudaEventRecord(ctx->lag_ev[k & 1], ctx->stream));
         if (k >= 1) {
             MFB_CUDA(cudaEventSynchronize(ctx->lag_ev[(k - 1) & 1]));
-            if (hslot[8 * ((k - 1) & 1) + SC_STOP] != 0.0) break;
+            if (hslot[8 * ((k - 1) & 1) + SC_STOP] != 0.0) {       // iteration k - 1 was the last: iteration k ran empty
+                MFB_CUDA(cudaStreamSynchronize(ctx->stream));       // its events must have completed before they are recycled
+                drop_after(marks[k & 1]);
+                break;
+            }
         }
     }
     MFB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -2388,12 +2413,12 @@ extern "C" int mfb_krylov_solve_ex(mfb_ctx* ctx, int method, int s, int maxiter,
     if (!ctx) return MFB_ERR_ARG;
     MFB_REQUIRE(ctx->U > 0 && ctx->K_total.p, MFB_ERR_STATE, "mfb_krylov_solve: pattern/matrix not built");
     MFB_REQUIRE(method >= MFB_IDRS && method <= MFB_IDRS_ORIGINAL, MFB_ERR_ARG, "unknown Krylov method");
-    MFB_REQUIRE(pr_mode >= MFB_PR_JACOBI && pr_mode <= MFB_PR_IDENTITY && pl_mode >= MFB_PL_IDENTITY && pl_mode <= MFB_PL_JACOBI_ROW,
+    MFB_REQUIRE(pr_mode >= MFB_PR_JACOBI && pr_mode <= MFB_PR_IDENTITY && pl_mode >= MFB_PL_IDENTITY && pl_mode <= MFB_PL_ILU,
                 MFB_ERR_ARG, "unknown preconditioner mode");
     MFB_REQUIRE(s >= 1 && (method == MFB_GMRES ? s + 1 <= MAXT : (2 * s + 2 <= MAXT && s + 2 <= MAXB && s <= MAXD)), MFB_ERR_ARG,
                 "s out of range");
-    MFB_REQUIRE(!(mfb_is_distributed(ctx) && (pr_mode == MFB_PR_JACOBI_COLUMN || pl_mode == MFB_PL_JACOBI_ROW)), MFB_ERR_ARG,
-                "row/column-norm Jacobi needs assembled rows: not available on a partitioned mesh");
+    MFB_REQUIRE(!(mfb_is_distributed(ctx) && (pr_mode == MFB_PR_JACOBI_COLUMN || pl_mode == MFB_PL_JACOBI_ROW || pl_mode == MFB_PL_ILU)), MFB_ERR_ARG,
+                "row/column-norm Jacobi and ILU need assembled rows: not available on a partitioned mesh");
     MFB_CUDA(cudaSetDevice(ctx->device));
     MFB_TRY(ensure_scalars(ctx));
     ProfScope ps(ctx, MFB_T_SOLVE);
@@ -2438,7 +2463,11 @@ extern "C" int mfb_krylov_solve_ex(mfb_ctx* ctx, int method, int s, int maxiter,
     }
     LAUNCH(k_scale_copy, nblk(nval), TPB, ctx->nodecol.p, ctx->K_total.p, ctx->jac.p, nval, nv, Ks.p);
     // ---- left preconditioner: Pl_Jacobi (:150-166), computed from the already right-scaled matrix (:38-40) ----
-    if (pl_mode != MFB_PL_IDENTITY) {
+    bool use_ilu = false;
+    if (pl_mode == MFB_PL_ILU) {                                 // Pl_ILU(A) on the right-scaled matrix (:38-40, 179-194)
+        MFB_TRY(mfb_ilu_factor(ctx, Ks.p, nullptr));
+        use_ilu = true;
+    } else if (pl_mode != MFB_PL_IDENTITY) {
         MFB_CUDA(plv.alloc(n));
         if (pl_mode == MFB_PL_JACOBI) {
             LAUNCH(k_jacobi_diag, nblk(n), TPB, ctx->nodeptr.p, ctx->nodecol.p, Ks.p, d_ok.p, ctx->N, nv, own, plv.p);
@@ -2462,6 +2491,7 @@ extern "C" int mfb_krylov_solve_ex(mfb_ctx* ctx, int method, int s, int maxiter,
     Solver S{ctx, n, Ks.p};
     S.n_global = ctx->n_global_nodes * nv;
     S.pl = plv.p;
+    S.pl_ilu = use_ilu;
     mfb_solve_info inf;
     memset(&inf, 0, sizeof(inf));
     {
@@ -2492,7 +2522,7 @@ extern "C" int mfb_krylov_solve_ex(mfb_ctx* ctx, int method, int s, int maxiter,
         }
         inf.iterations += it;
         MFB_TRY(true_residual(S, r, b, x, &res, false));        // the plain b - A x (:45-48)
-        if (S.pl) {                                              // left preconditioned: rescale the next pass's tolerance (:50-53)
+        if (S.has_pl()) {                                        // left preconditioned: rescale the next pass's tolerance (:50-53)
             MFB_TRY(S.Pl(r));
             double d;
             MFB_TRY(S.dot1(r, r, &d));

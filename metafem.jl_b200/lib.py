@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libmetafem_b200.so")
 MFB_OK, MFB_NOT_CONVERGED = 0, 1
 MFB_IDRS, MFB_BICGSTABL_GS, MFB_BICGSTABL, MFB_GMRES, MFB_CGS, MFB_CGS2, MFB_TFQMR, MFB_LSQR, MFB_IDRS_ORIGINAL = range(9)
 PR_JACOBI, PR_JACOBI_COLUMN, PR_IDENTITY = 0, 1, 2
-PL_IDENTITY, PL_JACOBI, PL_JACOBI_ROW = 0, 1, 2
+PL_IDENTITY, PL_JACOBI, PL_JACOBI_ROW, PL_ILU = 0, 1, 2, 3
 VEC_X, VEC_DX, VEC_X_STAR, VEC_RESIDUE = 0, 1, 2, 3
 MAT_K_LINEAR, MAT_K_TOTAL = 0, 1
 NUMBERING_SORTED, NUMBERING_REFERENCE = 0, 1
@@ -90,6 +90,7 @@ _SIGS = {
                                    C.POINTER(SolveInfo)]),
     "mfb_krylov_solve_ex": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                       _P, C.POINTER(SolveInfo)]),
+    "mfb_ilu_selftest": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int32), _P, C.c_int64]),
     "mfb_initialize_dx": (C.c_int, [_P, C.c_double, _P, C.c_int]),
     "mfb_update_x_star": (C.c_int, [_P, _P, C.c_int]),
     "mfb_update_dx": (C.c_int, [_P, _P, C.c_int, C.c_double]),

@@ -110,6 +110,41 @@ class Pl_Jacobi:
         return b
 
 
+class Pl_ILU:
+    """Pl_ILU(A) = ilu02!(copy(A)) + UnitLowerTriangular / UpperTriangular solves (02_Preconditioner.jl:179-194): zero-fill
+    incomplete LU of the CSR matrix in ITS row order without pivoting (what cuSPARSE csrilu02 computes), restated with plain loops
+    (small systems only)."""
+
+    def __init__(self, A):
+        import scipy.sparse as sps
+        n = A.shape[0]
+        M = sps.csr_matrix((A.data.copy(), A.col - 1, A.ptr - 1), shape=(n, n)) if hasattr(A, "ptr") else sps.csr_matrix(A, copy=True)
+        M.sort_indices()
+        ptr, col, val = M.indptr, M.indices, M.data
+        diag = np.full(n, -1)
+        for i in range(n):
+            where = {int(col[p]): p for p in range(ptr[i], ptr[i + 1])}
+            for p in range(ptr[i], ptr[i + 1]):              # IKJ over the lower entries in ascending column order
+                k = int(col[p])
+                if k >= i:
+                    break
+                val[p] /= val[diag[k]]
+                for q in range(diag[k] + 1, ptr[k + 1]):
+                    t = where.get(int(col[q]))
+                    if t is not None:
+                        val[t] -= val[p] * val[q]
+            diag[i] = where[i]
+        self.L = sps.tril(M, -1).tocsr() + sps.identity(n, format="csr")
+        self.U = sps.triu(M, 0).tocsr()
+        self.M = M
+
+    def __call__(self, b):
+        import scipy.sparse.linalg as spl
+        y = spl.spsolve_triangular(self.L, b, lower=True, unit_diagonal=True)
+        b[:] = spl.spsolve_triangular(self.U, y, lower=False)
+        return b
+
+
 def Identity(b):
     return b
 

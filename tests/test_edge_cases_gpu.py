@@ -67,7 +67,7 @@ def test_bad_kernel_source_and_unknown_method(built_lib):
         assert fd.ctx.lib.mfb_krylov_solve(fd.ctx.h, 99, 4, 10, 1, 1e-8, 1, None, C.byref(info)) == -3
         assert fd.ctx.lib.mfb_krylov_solve(fd.ctx.h, m.lib.MFB_IDRS, 40, 10, 1, 1e-8, 1, None, C.byref(info)) == -3   # s too large
         with pytest.raises(ValueError):
-            m.iterative_Solve(fd, Sv_func="idrs_original!")
+            m.iterative_Solve(fd, Sv_func="conjugate_gradient!")
         # one iteration cannot converge: MFB_NOT_CONVERGED (1) is a warning, the result is still delivered (02_Preconditioner.jl:66-68)
         delta = np.empty(dom.globalfield.basicfield_size)
         rc = fd.ctx.lib.mfb_krylov_solve(fd.ctx.h, m.lib.MFB_BICGSTABL_GS, 2, 1, 1, 1e-14, 1, m.lib.ptr(delta), C.byref(info))

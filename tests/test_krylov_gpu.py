@@ -88,3 +88,22 @@ def test_idrs_original_follows_the_reference_operation_by_operation(system):
     odelta = osv.iterative_Solve(dom, osv.idrs_original, max_pass=1, maxiter=iters, s=s, P=P)
     assert dom.last_solve["iters"] == [iters]
     assert np.linalg.norm(delta - odelta) <= 1e-8 * np.linalg.norm(odelta), np.linalg.norm(delta - odelta) / np.linalg.norm(odelta)
+
+
+def test_pl_ilu_factorisation_property_and_solve(system):
+    """Pl_ILU on the CUDA path: (L U)_ij = A_ij on the pattern (the defining property of a zero-fill incomplete factorisation,
+    checked by a device kernel on K_total), a few dozen dependency levels, and the left-preconditioned bicgstabl_GS! reaches the
+    same solution as the direct solve in fewer iterations than with the Jacobi scaling alone."""
+    import ctypes as C
+    import metafem_b200 as m
+    dom, fd, A, exact = system
+    defect, levels = C.c_double(1.0), C.c_int32(0)
+    fd.ctx.call("mfb_ilu_selftest", C.byref(defect), C.byref(levels), None, 0)
+    assert defect.value < 1e-12 and 1 <= levels.value < 200, (defect.value, levels.value)
+    # U^-1 L^-1 (A v) ~ v to the extent the factorisation is complete: a contraction, not an identity; it must at least beat Jacobi
+    delta = m.iterative_Solve(fd, Sv_func="bicgstabl_GS", Pl_func="Pl_ILU", maxiter=4000, max_pass=10, s=4, want_delta=True)
+    it_ilu = fd.last_solve["iterations"]
+    odelta = osv.iterative_Solve(dom, osv.bicgstabl_GS, max_pass=10, maxiter=4000, s=4, Pl_func=osv.Pl_ILU)
+    _check(dom, fd, A, exact, delta, odelta)
+    m.iterative_Solve(fd, Sv_func="bicgstabl_GS", maxiter=4000, max_pass=10, s=4)
+    assert it_ilu < fd.last_solve["iterations"], (it_ilu, fd.last_solve)
