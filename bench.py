@@ -282,7 +282,8 @@ class Env:
 def make_spec(name):
     from metafem_jl_b200.frontend import weakform as wf
     return {"neo_hookean": lambda: wf.neo_hookean(fixed_bg=1, traction_bg=2),
-            "linear_elasticity": lambda: wf.linear_elasticity(0.5769, 0.3846, 1000.0, fixed_bg=1, traction_bgs=((2, "sl"),)),
+            # E = 1e6, nu = 0.3 (lambda, mu = 0.5769e6, 0.3846e6), penalty 1000 E as in the cantilever script (3D_Script.jl:45-63)
+            "linear_elasticity": lambda: wf.linear_elasticity(0.5769e6, 0.3846e6, 1e9, fixed_bg=1, traction_bgs=((2, "sl"),)),
             "thermo_elasticity": lambda: wf.thermo_elasticity(fixed_bg=1, thermal_bg=2),
             "j2": lambda: wf.j2_plasticity(fixed_bg=1, traction_bg=2),
             "j2_fused": lambda: wf.j2_plasticity(fixed_bg=1, traction_bg=2, fused=True)}[name]()
@@ -336,7 +337,7 @@ class Case:
             fd.controlpoints["sl1"][:] = 120.0
             fd.globalfield.dt = 1.0
         else:
-            fd.controlpoints["sl1"][:] = 0.01
+            fd.controlpoints["sl1"][:] = 1e4
         fd.globalfield.converge_tol = WORKLOADS[name]["tol"]
         m.assemble_Global_Variables(fd)
         m.compile_Updater_GPU(1, fd)

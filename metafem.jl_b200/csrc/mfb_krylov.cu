@@ -485,7 +485,9 @@ __global__ void k_reduce_partials(const double* partials, int nb, double* out) {
 // then the per-method arrays (SC_SIG ... for bicgstabl_GS!, ID_* for idrs!).
 enum { SC_RHO0 = 0, SC_ALPHA = 1, SC_OMEGA = 2, SC_BETA = 3, SC_RES2 = 4, SC_STOP = 5, SC_ITER = 6, SC_SIG = 8, SC_GAMP = 24,
        SC_GAM = 40, SC_GAMPP = 56, SC_TAU = 72, SC_COUNT = 72 + 16 * 16 };
-enum { OP_NONE = 0, OP_BETA0, OP_BETA, OP_ALPHA, OP_TAU, OP_SIG, OP_FINAL };
+enum { OP_NONE = 0, OP_BETA0, OP_BETA, OP_ALPHA, OP_TAU, OP_SIG, OP_FINAL,
+       OP_IDR_FC, OP_IDR_ALPHA, OP_IDR_M, OP_IDR_RES, OP_IDR_OMEGA };
+enum { IDS_OMEGA = 0, IDS_BETA = 1, IDS_ALPHA = 2, IDS_F = 8 };   // idrs! scalars: f [8..8+S), c, -omega c, M [S][S] behind them
 struct ScOp { int op, i, j, off; };
 struct RedCtx {
     double* sc;          // device scalars (nullptr: no stop flag, no scalar ops)
@@ -524,6 +526,16 @@ __device__ void sc_gamma(double* sc, int S) {                                   
 }
 
 // scalar recurrences of bicgstabl_GS! (03_BiCGstabl.jl:43-93), applied by ONE thread to freshly reduced values rd[]
+// c = LowerTriangular(M[k:s,k:s]) \ f[k:s] and -omega c (04_IDRs.jl:52)
+__device__ void idr_csolve(double* sc, int k, int S) {
+    double* f = sc + IDS_F; double* c = f + S; double* oc = f + 2 * S; const double* M = f + 3 * S;
+    for (int i = k; i < S; ++i) {
+        double v = f[i];
+        for (int j = k; j < i; ++j) v -= M[i * S + j] * c[j];
+        c[i] = v / M[i * S + i];
+        oc[i] = -sc[IDS_OMEGA] * c[i];
+    }
+}
 __device__ void sc_apply(const RedCtx& R, const ScOp& o, const double* red) {
     double* sc = R.sc;
     const int S = R.S;
@@ -558,6 +570,40 @@ __device__ void sc_apply(const RedCtx& R, const ScOp& o, const double* red) {
                 sc[SC_BETA] = sc[SC_ALPHA] * rho1 / sc[SC_RHO0];
                 sc[SC_RHO0] = rho1;
             }
+        } break;
+        // ---- idrs! (04_IDRs.jl:26-95): f [IDS_F + i], c [IDS_F + S + i], -omega c [IDS_F + 2S + i], M [IDS_F + 3S + i S + k] ----
+        case OP_IDR_FC:                                  // o.i == 1: f = P' r first (:47-49); then c of inner step o.j
+            if (o.i == 1)
+                for (int i = 0; i < S; ++i) sc[IDS_F + i] = rd[i];
+            idr_csolve(sc, o.j, S);
+            break;
+        case OP_IDR_ALPHA: sc[IDS_ALPHA] = rd[0] / sc[IDS_F + 3 * S + o.i * S + o.i]; break;           // (:66)
+        case OP_IDR_M: {                                 // M[i][k] = P[i]' G[k], i >= k (:71-73); beta (:76); f update (:85)
+            double* f = sc + IDS_F; double* M = f + 3 * S;
+            const int k = o.j;
+            for (int i = k; i < S; ++i) M[i * S + k] = rd[i - k];
+            const double beta = f[k] / M[k * S + k];
+            sc[IDS_BETA] = beta;
+            for (int i = k + 1; i < S; ++i) f[i] -= beta * M[i * S + k];
+        } break;
+        case OP_IDR_RES: {                               // convergence test after an inner step (:81-84, :92-93); o.j = next k or -1
+            const double n2 = rd[0];
+            sc[SC_RES2] = n2;
+            const double nrm = sqrt(n2) * R.inv_sqrt_n;
+            if (!(nrm > R.tol) || sc[SC_ITER] >= (double)R.maxiter) {
+                sc[SC_STOP] = 1.0;
+            } else {
+                sc[SC_ITER] += 1.0;
+                if (o.j >= 0) idr_csolve(sc, o.j, S);      // c of the next inner step
+            }
+        } break;
+        case OP_IDR_OMEGA: {                             // modify_Omega (:1-8) from |Ar|^2, |r|^2, Ar'r
+            const double n1 = sqrt(rd[0]), n2 = sqrt(rd[1]), d = rd[2];
+            const double angle = 0.70710678118654752440;
+            const double rho = fabs(d / (n1 * n2));
+            double omega = d / (n1 * n1);
+            if (rho < angle) omega = omega * angle / rho;
+            sc[IDS_OMEGA] = omega;
         } break;
         default: break;
     }
@@ -1188,6 +1234,7 @@ __global__ void k_idr_init(double* sc, int S) {
     __syncthreads();
     if (threadIdx.x == 0) {
         sc[ID_OMEGA] = 1.0;
+        sc[6] = 1.0;                                                           // SC_ITER (the fused path counts on the device)
         for (int i = 0; i < S; ++i) sc[8 + 3 * S + i * S + i] = 1.0;           // M = I (:41)
     }
 }
@@ -1605,8 +1652,8 @@ int true_residual(Solver& S, double* r, const double* b, const double* x, double
 // idrs!  (04_IDRs.jl:26-95). Vectors: P[s], U[s], G[s], Ar. Same operations in the same order as the reference; M, f, c,
 // omega, alpha, beta live on the device (one-thread kernels between the vector kernels): one host synchronisation per
 // inner step -- the convergence test the reference makes there -- instead of one per dot product (k + 3 of them).
-int idrs(Solver& S, double* x, const double* b, double* r, double tol, int maxiter, int s, uint64_t seed, int pass,
-         std::vector<double*>& W, int* iters) {
+int idrs_legacy(Solver& S, double* x, const double* b, double* r, double tol, int maxiter, int s, uint64_t seed, int pass,
+                std::vector<double*>& W, int* iters) {
     mfb_ctx* ctx = S.ctx;
     const int64_t n = S.n;
     double res;
@@ -1904,6 +1951,126 @@ int bicgstabl_gs(Solver& S, double* x, const double* b, double* r, double tol, i
     }
     MFB_CUDA(cudaStreamSynchronize(ctx->stream));
     // the launches enqueued after the stop flag went up did nothing: the newest slot holds the final scalars
+    const double* fs = hslot[8 + SC_ITER] >= hslot[SC_ITER] ? hslot + 8 : hslot;
+    *iters = (int)fs[SC_ITER];
+    return MFB_OK;
+}
+
+// idrs!  (04_IDRs.jl:26-95), fused form: same operations in the same order; every reduction rides in the kernel that produces its
+// operand, the small recurrences (f, c, M, alpha, beta, omega, the convergence test) run in the tails of those kernels, and the
+// host reads the stop flag back once per cycle of s + 1 inner steps, one cycle late. Launches per cycle: 4 s + s (s - 1) / 2 + 3
+// (63 for s = 8, i.e. 7 per SpMV; round 1: ~21 per SpMV and one host synchronisation per inner step).
+int idrs(Solver& S, double* x, const double* b, double* r, double tol, int maxiter, int s, uint64_t seed, int pass,
+         std::vector<double*>& W, int* iters) {
+    mfb_ctx* ctx = S.ctx;
+    const int64_t n = S.n;
+    double res;
+    MFB_TRY(true_residual(S, r, b, x, &res));
+    if (res <= tol) { *iters = 0; return MFB_OK; }
+    double** P = &W[0];
+    double** U = &W[s];
+    double** G = &W[2 * s];
+    double* Ar = W[3 * s];
+    for (int k = 0; k < s; ++k) {
+        LAUNCH(k_rand, RED_BLOCKS, TPB, P[k], n, (unsigned long long)seed, (unsigned long long)(pass * 64 + k), ctx->gid.p, ctx->n_var);
+        MFB_CUDA(cudaMemsetAsync(U[k], 0, n * sizeof(double), ctx->stream));
+        MFB_CUDA(cudaMemsetAsync(G[k], 0, n * sizeof(double), ctx->stream));
+    }
+    MFB_CUDA(ctx->ksc.alloc(SC_COUNT > 8 + 3 * MAXD + MAXD * MAXD ? SC_COUNT : 8 + 3 * MAXD + MAXD * MAXD));
+    double* sc = ctx->ksc.p;
+    LAUNCH(k_idr_init, 1, 128, sc, s);                      // omega = 1, M = I, STOP = 0, ITER = 1
+    S.f_tol = tol; S.f_maxiter = maxiter; S.f_S = s;
+    const double* cdev = sc + IDS_F + s;                    // c[i]
+    const double* ocdev = sc + IDS_F + 2 * s;               // -omega c[i]
+    S.progs.clear();
+    auto add = [&](const FB& fb) { S.progs.push_back(fb.F); return (int)S.progs.size() - 1; };
+    FB f0;                                                  // f = P' r, c of k = 0 (opening of the first cycle)
+    for (int i = 0; i < s; ++i) f0.dot(P[i], r);
+    f0.op(0, OP_IDR_FC, 1, 0, 0);
+    const int p_f0 = add(f0);
+    std::vector<int> pB(s), pD(s), pE(s);
+    std::vector<std::vector<int>> pC(s);
+    for (int k = 0; k < s; ++k) {
+        FB B;                                               // U[k] = c_k U[k] + sum_{i>k} c_i U[i] + omega (r - sum_{i>=k} c_i G[i])  (:53-63)
+        B.upd(U[k], 1.0, cdev + k);
+        for (int i = k; i < s; ++i) {
+            if (i != k) B.term(1.0, cdev + i, U[i]);
+            B.term(1.0, ocdev + i, G[i]);
+        }
+        B.term(1.0, sc + IDS_OMEGA, r);
+        pB[k] = add(B);
+        FB D;                                               // after G[k] = A U[k]: alpha_0 (k > 0) or the whole column M[., 0]
+        if (k == 0) { for (int i = 0; i < s; ++i) D.dot(P[i], G[0]); D.op(0, OP_IDR_M, 0, 0, 0); }
+        else D.dot(P[0], G[k]).op(0, OP_IDR_ALPHA, 0, 0, 0);
+        pD[k] = add(D);
+        for (int i = 0; i < k; ++i) {                       // G[k] -= alpha G[i]; U[k] -= alpha U[i]  (:65-69), next alpha or M[., k]
+            FB Cp;
+            Cp.upd(U[k], 1.0).term(-1.0, sc + IDS_ALPHA, U[i]);
+            Cp.upd(G[k], 1.0).term(-1.0, sc + IDS_ALPHA, G[i]);          // last update: the dots below see the new G[k]
+            if (i + 1 < k) Cp.dot(P[i + 1], nullptr).op(0, OP_IDR_ALPHA, i + 1, 0, 0);
+            else { for (int q = k; q < s; ++q) Cp.dot(P[q], nullptr); Cp.op(0, OP_IDR_M, 0, k, 0); }
+            pC[k].push_back(add(Cp));
+        }
+        FB E;                                               // x += beta U[k]; r -= beta G[k]; ||r||^2  (:77-80)
+        E.upd(x, 1.0).term(1.0, sc + IDS_BETA, U[k]);
+        E.upd(r, 1.0).term(-1.0, sc + IDS_BETA, G[k]);
+        E.dot(nullptr, nullptr).op(0, OP_IDR_RES, 0, k + 1 < s ? k + 1 : -1, 0);
+        pE[k] = add(E);
+    }
+    FB Fo;                                                  // omega from Ar = A r  (:87-88)
+    Fo.dot(Ar, Ar).dot(r, r).dot(Ar, r).op(0, OP_IDR_OMEGA, 0, 0, 0);
+    const int p_om = add(Fo);
+    FB Gp;                                                  // x += omega r; r -= omega Ar; ||r||^2; f = P' r and c of the next cycle  (:89-93)
+    Gp.upd(x, 1.0).term(1.0, sc + IDS_OMEGA, r);
+    Gp.upd(r, 1.0).term(-1.0, sc + IDS_OMEGA, Ar);
+    Gp.dot(nullptr, nullptr);
+    for (int i = 0; i < s; ++i) Gp.dot(P[i], nullptr);
+    Gp.op(0, OP_IDR_RES, 0, -1, 0).op(1, OP_IDR_FC, 1, 0, 1);
+    const int p_end = add(Gp);
+    MFB_TRY(S.upload_programs());
+    for (int q = 0; q < 2; ++q)
+        if (!ctx->lag_ev[q]) MFB_CUDA(cudaEventCreateWithFlags(&ctx->lag_ev[q], cudaEventDisableTiming));
+    double* hslot = ctx->h_scal + 32;
+    MFB_TRY(S.run(p_f0));
+    struct Mark { size_t ev[MFB_T_COUNT][2]; int spmv; int64_t launches; } marks[2];
+    auto take_mark = [&](Mark& m) {
+        for (int q = 0; q < MFB_T_COUNT; ++q) { m.ev[q][0] = ctx->prof[q].start.size(); m.ev[q][1] = ctx->prof[q].stop.size(); }
+        m.spmv = S.spmv; m.launches = ctx->launches;
+    };
+    auto drop_after = [&](const Mark& m) {
+        for (int q = 0; q < MFB_T_COUNT; ++q) {
+            if (q == MFB_T_SOLVE) continue;
+            ProfEvents& Pe = ctx->prof[q];
+            while (Pe.start.size() > m.ev[q][0]) { ctx->event_pool.push_back(Pe.start.back()); Pe.start.pop_back(); }
+            while (Pe.stop.size() > m.ev[q][1]) { ctx->event_pool.push_back(Pe.stop.back()); Pe.stop.pop_back(); }
+        }
+        S.spmv = m.spmv; ctx->launches = m.launches;
+    };
+    const ScOp none{OP_NONE, 0, 0, 0};
+    for (int cyc = 0;; ++cyc) {
+        take_mark(marks[cyc & 1]);
+        for (int k = 0; k < s; ++k) {
+            MFB_TRY(S.run(pB[k]));
+            MFB_TRY(S.mul_dot(G[k], U[k], nullptr, none, -1));
+            MFB_TRY(S.run(pD[k]));
+            for (int pc : pC[k]) MFB_TRY(S.run(pc));
+            MFB_TRY(S.run(pE[k]));
+        }
+        MFB_TRY(S.mul_dot(Ar, r, nullptr, none, -1));
+        MFB_TRY(S.run(p_om));
+        MFB_TRY(S.run(p_end));
+        MFB_CUDA(cudaMemcpyAsync(hslot + 8 * (cyc & 1), sc, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        MFB_CUDA(cudaEventRecord(ctx->lag_ev[cyc & 1], ctx->stream));
+        if (cyc >= 1) {
+            MFB_CUDA(cudaEventSynchronize(ctx->lag_ev[(cyc - 1) & 1]));
+            if (hslot[8 * ((cyc - 1) & 1) + SC_STOP] != 0.0) {
+                MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+                drop_after(marks[cyc & 1]);
+                break;
+            }
+        }
+    }
+    MFB_CUDA(cudaStreamSynchronize(ctx->stream));
     const double* fs = hslot[8 + SC_ITER] >= hslot[SC_ITER] ? hslot + 8 : hslot;
     *iters = (int)fs[SC_ITER];
     return MFB_OK;
@@ -2507,7 +2674,10 @@ extern "C" int mfb_krylov_solve_ex(mfb_ctx* ctx, int method, int s, int maxiter,
         int it = 0;
         const double ptol = tol_factor * tol;
         switch (method) {
-            case MFB_IDRS: MFB_TRY(idrs(S, x, b, r, ptol, maxiter, s, seed, pass, W, &it)); break;
+            case MFB_IDRS:
+                if (legacy) MFB_TRY(idrs_legacy(S, x, b, r, ptol, maxiter, s, seed, pass, W, &it));
+                else MFB_TRY(idrs(S, x, b, r, ptol, maxiter, s, seed, pass, W, &it));
+                break;
             case MFB_BICGSTABL_GS:
                 if (legacy) MFB_TRY(bicgstabl_gs_legacy(S, x, b, r, ptol, maxiter, s, seed, pass, W, &it));
                 else MFB_TRY(bicgstabl_gs(S, x, b, r, ptol, maxiter, s, seed, pass, W, &it));

@@ -470,15 +470,12 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
                 }
             }
         } else if constexpr (F::HAS_RES) {
-            // residual-only kernels (_Res_Basic)
-            constexpr int QS = (TPB / (NA * NV)) < 1 ? 1 : ((TPB / (NA * NV)) > 4 ? 4 : (TPB / (NA * NV)));   // q-range split
-            constexpr int QCH = (NQ + QS - 1) / QS;
-            for (int i = tid; i < NA * NV * QS; i += TPB) {
-                const int part = i / (NA * NV), j = i - part * (NA * NV);
-                const int v = j % NV, a = j / NV;
-                const int q1 = (part + 1) * QCH < NQ ? (part + 1) * QCH : NQ;
+            // residual-only kernels (_Res_Basic): ONE add per (element, node, variable) -- the deterministic scatter relies on
+            // every accumulator receiving at most two adds, so the q range is not split over threads
+            for (int i = tid; i < NA * NV; i += TPB) {
+                const int v = i % NV, a = i / NV;
                 double s = 0.0;
-                for (int q = part * QCH; q < q1; ++q) {
+                for (int q = 0; q < NQ; ++q) {
 #pragma unroll
                     for (int k = 0; k < NGS; ++k) s += S.gd.G[q][k][a] * S.gu[q][v * 4 + F::gslot_id(k)];
                 }
