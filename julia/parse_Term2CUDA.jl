@@ -264,7 +264,7 @@ function gen_Form_CUDA(name::String, tb::TensorTable, asm_wf::AssembleWeakform, 
     ke = 8 * (has_K ? mrows * n_a : 1)
     nvl = (linear ? 0 : L1 * nv) + length(fields)
     geo = align16(max(8 * n_q * (9 + 1 + 3), has_K ? 4 * n_a * n_a : 4))
-    smem = align16(align16(max(gd, ke)) + geo + 8 * (n_q * 4 * max(nvl, 1) + n_a * 3 + L1 * n_a * nv + max(length(fields), 1) * n_a) + 8 * n_a)
+    smem = align16(align16(max(gd, ke)) + geo + 8 * (n_q * 4 * max(nvl, 1) + n_a * 3 + L1 * n_a * nv + max(length(fields), 1) * n_a) + 4 * n_a)
     body = replace(join(io, "\n"), "@SMEM@" => string(smem))
     return FormText(body, fields, globs, smem, has_K, tpb, string.(qp_words), [n for (_, n) in qpo]), st.qp_calls
 end

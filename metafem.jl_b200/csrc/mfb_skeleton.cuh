@@ -202,7 +202,6 @@ struct Smem {
     double xe[F::NA][3];
     double ue[F::L1][F::NA][F::NV];
     double ce[F::NC > 0 ? F::NC : 1][F::NA];
-    int node[F::NA];
     int rnode[F::NA];                              // residual scatter target of every local node
 };
 
@@ -230,7 +229,6 @@ __device__ __forceinline__ void assemble(const MfbArgs& A) {
         // ---- phase A: gather node data ----------------------------------------------------
         for (int a = tid; a < NA; a += TPB) {
             int g = A.conn[e * NA + a];
-            S.node[a] = g;
             S.rnode[a] = A.rmap[e * NA + a];
             S.xe[a][0] = A.xyz[3 * (size_t)g + 0];
             S.xe[a][1] = A.xyz[3 * (size_t)g + 1];

@@ -19,10 +19,13 @@ def _slot(sd):
     return 0 if not sd else int(sd[0])
 
 
-def _tile(n_a, nv, max_acc=60):
+def _tile(n_a, nv, max_acc=None):
     """Tangent tiling: one lane owns the rows (a, dp, bp = 0..NV-1) and NTC columns of the element matrix, i.e. NV*NTC
     FP64 accumulators; CG column groups cover the NA columns (NTC even for 128-bit operand loads). The NA*NV*CG tiles
     are dealt to W warps, LPW active lanes each."""
+    import os
+    if max_acc is None:
+        max_acc = int(os.environ.get("MFB_MAX_ACC", "60"))       # experiments: 30 = half-width tiles on twice the warps
     cg = 1
     while True:
         ntc = -(-n_a // cg)
@@ -164,7 +167,7 @@ def _form(name, spec, blk, n_a, n_q, linear, evalk=False):
     nvl = (0 if linear else L1 * nv) + len(fields)
     geo = _align16(max(8 * n_q * (9 + 1 + 3), 4 * n_a * n_a if terms else 4))
     smem = _align16(_align16(max(gd, ke)) + geo + 8 * (n_q * 4 * max(nvl, 1) + n_a * 3 + L1 * n_a * nv
-                                                      + max(len(fields), 1) * n_a) + 8 * n_a)
+                                                      + max(len(fields), 1) * n_a) + 4 * n_a)
     body = "\n".join(lines).replace("@SMEM@", str(smem))
     return body, fields, globs, smem, bool(terms), tpb, qp_in_names, qp_out_names
 
@@ -183,6 +186,7 @@ def _min_blocks(tpb, smem, regs=170):
     import os
     if os.environ.get("MFB_MINB"):
         return int(os.environ["MFB_MINB"])
+    regs = int(os.environ.get("MFB_REGS", regs))
     return max(1, min(232448 // (smem + 1024), 65536 // (tpb * regs), 32))
 
 

@@ -1,7 +1,7 @@
 #include "mfb_skeleton.cuh"
 
 struct F_b0_lin {
-  static constexpr int NV = 3, NA = 20, NQ = 27, L1 = 3, BOUNDARY = 0, LINEAR = 1, NW = 0, NCW = 0, NC = 0, HAS_RES = 0, HAS_K = 1, TPB = 64, NSD = 4, KS = 4, ND = 144, NTC = 20, CG = 1, W = 2, LPW = 30, SMEM = 54304, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 4;
+  static constexpr int NV = 3, NA = 20, NQ = 27, L1 = 3, BOUNDARY = 0, LINEAR = 1, NW = 0, NCW = 0, NC = 0, HAS_RES = 0, HAS_K = 1, TPB = 64, NSD = 4, KS = 4, ND = 144, NTC = 20, CG = 1, W = 2, LPW = 30, SMEM = 54224, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 4;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {0, 1, 2, 3}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {0, 1, 2, 3}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {0, 1, 2, 3}; return t[i]; }
@@ -38,7 +38,7 @@ struct F_b0_lin {
 extern "C" __global__ void __launch_bounds__(64, 4) mfb_b0_lin(const MfbArgs A) { mfb::assemble<F_b0_lin>(A); }
 
 struct F_b0_nl {
-  static constexpr int NV = 3, NA = 20, NQ = 27, L1 = 3, BOUNDARY = 0, LINEAR = 0, NW = 15, NCW = 0, NC = 0, HAS_RES = 1, HAS_K = 0, TPB = 64, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 30336, EVAL = 0, NQPI = 6, NQPO = 0, NGS = 4;
+  static constexpr int NV = 3, NA = 20, NQ = 27, L1 = 3, BOUNDARY = 0, LINEAR = 0, NW = 15, NCW = 0, NC = 0, HAS_RES = 1, HAS_K = 0, TPB = 64, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 30256, EVAL = 0, NQPI = 6, NQPO = 0, NGS = 4;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {0, 1, 2, 3}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {0, 1, 2, 3}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {0}; return t[i]; }
@@ -90,7 +90,7 @@ struct F_b0_nl {
 extern "C" __global__ void __launch_bounds__(64, 6) mfb_b0_nl(const MfbArgs A) { mfb::assemble<F_b0_nl>(A); }
 
 struct F_b0_ev {
-  static constexpr int NV = 3, NA = 20, NQ = 27, L1 = 3, BOUNDARY = 0, LINEAR = 0, NW = 15, NCW = 0, NC = 0, HAS_RES = 0, HAS_K = 0, TPB = 64, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 17376, EVAL = 1, NQPI = 0, NQPO = 6, NGS = 0;
+  static constexpr int NV = 3, NA = 20, NQ = 27, L1 = 3, BOUNDARY = 0, LINEAR = 0, NW = 15, NCW = 0, NC = 0, HAS_RES = 0, HAS_K = 0, TPB = 64, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 17296, EVAL = 1, NQPI = 0, NQPO = 6, NGS = 0;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {-1, -1, -1, -1}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {0}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {0}; return t[i]; }
@@ -129,7 +129,7 @@ struct F_b0_ev {
 extern "C" __global__ void __launch_bounds__(64, 6) mfb_b0_ev(const MfbArgs A) { mfb::assemble<F_b0_ev>(A); }
 
 struct F_b1_lin {
-  static constexpr int NV = 3, NA = 20, NQ = 9, L1 = 3, BOUNDARY = 1, LINEAR = 1, NW = 0, NCW = 3, NC = 3, HAS_RES = 0, HAS_K = 1, TPB = 64, NSD = 1, KS = 1, ND = 9, NTC = 20, CG = 1, W = 2, LPW = 30, SMEM = 33824, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
+  static constexpr int NV = 3, NA = 20, NQ = 9, L1 = 3, BOUNDARY = 1, LINEAR = 1, NW = 0, NCW = 3, NC = 3, HAS_RES = 0, HAS_K = 1, TPB = 64, NSD = 1, KS = 1, ND = 9, NTC = 20, CG = 1, W = 2, LPW = 30, SMEM = 33744, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {0, -1, -1, -1}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {0}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {0}; return t[i]; }
@@ -151,7 +151,7 @@ struct F_b1_lin {
 extern "C" __global__ void __launch_bounds__(64, 6) mfb_b1_lin(const MfbArgs A) { mfb::assemble<F_b1_lin>(A); }
 
 struct F_b1_nl {
-  static constexpr int NV = 3, NA = 20, NQ = 9, L1 = 3, BOUNDARY = 1, LINEAR = 0, NW = 3, NCW = 3, NC = 3, HAS_RES = 1, HAS_K = 0, TPB = 64, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 8480, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
+  static constexpr int NV = 3, NA = 20, NQ = 9, L1 = 3, BOUNDARY = 1, LINEAR = 0, NW = 3, NCW = 3, NC = 3, HAS_RES = 1, HAS_K = 0, TPB = 64, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 8400, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {0, -1, -1, -1}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {0}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {0}; return t[i]; }
@@ -176,7 +176,7 @@ struct F_b1_nl {
 extern "C" __global__ void __launch_bounds__(64, 6) mfb_b1_nl(const MfbArgs A) { mfb::assemble<F_b1_nl>(A); }
 
 struct F_b2_nl {
-  static constexpr int NV = 3, NA = 20, NQ = 9, L1 = 3, BOUNDARY = 1, LINEAR = 0, NW = 0, NCW = 6, NC = 6, HAS_RES = 1, HAS_K = 0, TPB = 64, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 9824, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
+  static constexpr int NV = 3, NA = 20, NQ = 9, L1 = 3, BOUNDARY = 1, LINEAR = 0, NW = 0, NCW = 6, NC = 6, HAS_RES = 1, HAS_K = 0, TPB = 64, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 9744, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {0, -1, -1, -1}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {0}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {0}; return t[i]; }

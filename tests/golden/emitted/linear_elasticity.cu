@@ -1,7 +1,7 @@
 #include "mfb_skeleton.cuh"
 
 struct F_b0_lin {
-  static constexpr int NV = 3, NA = 20, NQ = 27, L1 = 1, BOUNDARY = 0, LINEAR = 1, NW = 0, NCW = 0, NC = 0, HAS_RES = 0, HAS_K = 1, TPB = 64, NSD = 3, KS = 3, ND = 81, NTC = 20, CG = 1, W = 2, LPW = 30, SMEM = 36064, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 3;
+  static constexpr int NV = 3, NA = 20, NQ = 27, L1 = 1, BOUNDARY = 0, LINEAR = 1, NW = 0, NCW = 0, NC = 0, HAS_RES = 0, HAS_K = 1, TPB = 64, NSD = 3, KS = 3, ND = 81, NTC = 20, CG = 1, W = 2, LPW = 30, SMEM = 35984, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 3;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {-1, 0, 1, 2}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {1, 2, 3}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {1, 2, 3}; return t[i]; }
@@ -38,7 +38,7 @@ struct F_b0_lin {
 extern "C" __global__ void __launch_bounds__(64, 6) mfb_b0_lin(const MfbArgs A) { mfb::assemble<F_b0_lin>(A); }
 
 struct F_b0_nl {
-  static constexpr int NV = 3, NA = 20, NQ = 27, L1 = 1, BOUNDARY = 0, LINEAR = 0, NW = 9, NCW = 0, NC = 0, HAS_RES = 1, HAS_K = 0, TPB = 64, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 19872, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 3;
+  static constexpr int NV = 3, NA = 20, NQ = 27, L1 = 1, BOUNDARY = 0, LINEAR = 0, NW = 9, NCW = 0, NC = 0, HAS_RES = 1, HAS_K = 0, TPB = 64, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 19792, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 3;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {-1, 0, 1, 2}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {1, 2, 3}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {0}; return t[i]; }
@@ -78,7 +78,7 @@ struct F_b0_nl {
 extern "C" __global__ void __launch_bounds__(64, 6) mfb_b0_nl(const MfbArgs A) { mfb::assemble<F_b0_nl>(A); }
 
 struct F_b1_lin {
-  static constexpr int NV = 3, NA = 20, NQ = 9, L1 = 1, BOUNDARY = 1, LINEAR = 1, NW = 0, NCW = 3, NC = 3, HAS_RES = 0, HAS_K = 1, TPB = 64, NSD = 1, KS = 1, ND = 9, NTC = 20, CG = 1, W = 2, LPW = 30, SMEM = 32864, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
+  static constexpr int NV = 3, NA = 20, NQ = 9, L1 = 1, BOUNDARY = 1, LINEAR = 1, NW = 0, NCW = 3, NC = 3, HAS_RES = 0, HAS_K = 1, TPB = 64, NSD = 1, KS = 1, ND = 9, NTC = 20, CG = 1, W = 2, LPW = 30, SMEM = 32784, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {0, -1, -1, -1}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {0}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {0}; return t[i]; }
@@ -100,7 +100,7 @@ struct F_b1_lin {
 extern "C" __global__ void __launch_bounds__(64, 6) mfb_b1_lin(const MfbArgs A) { mfb::assemble<F_b1_lin>(A); }
 
 struct F_b1_nl {
-  static constexpr int NV = 3, NA = 20, NQ = 9, L1 = 1, BOUNDARY = 1, LINEAR = 0, NW = 3, NCW = 3, NC = 3, HAS_RES = 1, HAS_K = 0, TPB = 64, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 5792, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
+  static constexpr int NV = 3, NA = 20, NQ = 9, L1 = 1, BOUNDARY = 1, LINEAR = 0, NW = 3, NCW = 3, NC = 3, HAS_RES = 1, HAS_K = 0, TPB = 64, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 5712, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {0, -1, -1, -1}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {0}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {0}; return t[i]; }
@@ -125,7 +125,7 @@ struct F_b1_nl {
 extern "C" __global__ void __launch_bounds__(64, 6) mfb_b1_nl(const MfbArgs A) { mfb::assemble<F_b1_nl>(A); }
 
 struct F_b2_nl {
-  static constexpr int NV = 3, NA = 20, NQ = 9, L1 = 1, BOUNDARY = 1, LINEAR = 0, NW = 0, NCW = 6, NC = 6, HAS_RES = 1, HAS_K = 0, TPB = 64, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 7136, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
+  static constexpr int NV = 3, NA = 20, NQ = 9, L1 = 1, BOUNDARY = 1, LINEAR = 0, NW = 0, NCW = 6, NC = 6, HAS_RES = 1, HAS_K = 0, TPB = 64, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 7056, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {0, -1, -1, -1}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {0}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {0}; return t[i]; }

@@ -1,7 +1,7 @@
 #include "mfb_skeleton.cuh"
 
 struct F_b0_lin {
-  static constexpr int NV = 1, NA = 10, NQ = 14, L1 = 1, BOUNDARY = 0, LINEAR = 1, NW = 0, NCW = 1, NC = 1, HAS_RES = 0, HAS_K = 1, TPB = 64, NSD = 3, KS = 3, ND = 9, NTC = 10, CG = 1, W = 1, LPW = 10, SMEM = 6864, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 3;
+  static constexpr int NV = 1, NA = 10, NQ = 14, L1 = 1, BOUNDARY = 0, LINEAR = 1, NW = 0, NCW = 1, NC = 1, HAS_RES = 0, HAS_K = 1, TPB = 64, NSD = 3, KS = 3, ND = 9, NTC = 10, CG = 1, W = 1, LPW = 10, SMEM = 6832, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 3;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {-1, 0, 1, 2}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {1, 2, 3}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {1, 2, 3}; return t[i]; }
@@ -21,7 +21,7 @@ struct F_b0_lin {
 extern "C" __global__ void __launch_bounds__(64, 6) mfb_b0_lin(const MfbArgs A) { mfb::assemble<F_b0_lin>(A); }
 
 struct F_b0_nl {
-  static constexpr int NV = 1, NA = 10, NQ = 14, L1 = 1, BOUNDARY = 0, LINEAR = 0, NW = 3, NCW = 1, NC = 1, HAS_RES = 1, HAS_K = 0, TPB = 64, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 7424, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 4;
+  static constexpr int NV = 1, NA = 10, NQ = 14, L1 = 1, BOUNDARY = 0, LINEAR = 0, NW = 3, NCW = 1, NC = 1, HAS_RES = 1, HAS_K = 0, TPB = 64, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 7392, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 4;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {0, 1, 2, 3}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {0, 1, 2, 3}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {0}; return t[i]; }
@@ -45,7 +45,7 @@ struct F_b0_nl {
 extern "C" __global__ void __launch_bounds__(64, 6) mfb_b0_nl(const MfbArgs A) { mfb::assemble<F_b0_nl>(A); }
 
 struct F_b1_lin {
-  static constexpr int NV = 1, NA = 10, NQ = 7, L1 = 1, BOUNDARY = 1, LINEAR = 1, NW = 0, NCW = 0, NC = 0, HAS_RES = 0, HAS_K = 1, TPB = 64, NSD = 1, KS = 1, ND = 1, NTC = 10, CG = 1, W = 1, LPW = 10, SMEM = 2240, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
+  static constexpr int NV = 1, NA = 10, NQ = 7, L1 = 1, BOUNDARY = 1, LINEAR = 1, NW = 0, NCW = 0, NC = 0, HAS_RES = 0, HAS_K = 1, TPB = 64, NSD = 1, KS = 1, ND = 1, NTC = 10, CG = 1, W = 1, LPW = 10, SMEM = 2208, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {0, -1, -1, -1}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {0}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {0}; return t[i]; }
@@ -62,7 +62,7 @@ struct F_b1_lin {
 extern "C" __global__ void __launch_bounds__(64, 6) mfb_b1_lin(const MfbArgs A) { mfb::assemble<F_b1_lin>(A); }
 
 struct F_b1_nl {
-  static constexpr int NV = 1, NA = 10, NQ = 7, L1 = 1, BOUNDARY = 1, LINEAR = 0, NW = 1, NCW = 0, NC = 0, HAS_RES = 1, HAS_K = 0, TPB = 64, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 2064, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
+  static constexpr int NV = 1, NA = 10, NQ = 7, L1 = 1, BOUNDARY = 1, LINEAR = 0, NW = 1, NCW = 0, NC = 0, HAS_RES = 1, HAS_K = 0, TPB = 64, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 2032, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {0, -1, -1, -1}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {0}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {0}; return t[i]; }

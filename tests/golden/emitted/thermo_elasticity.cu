@@ -1,7 +1,7 @@
 #include "mfb_skeleton.cuh"
 
 struct F_b0_lin {
-  static constexpr int NV = 4, NA = 20, NQ = 27, L1 = 2, BOUNDARY = 0, LINEAR = 1, NW = 0, NCW = 0, NC = 0, HAS_RES = 0, HAS_K = 1, TPB = 160, NSD = 4, KS = 4, ND = 256, NTC = 10, CG = 2, W = 5, LPW = 32, SMEM = 78336, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 4;
+  static constexpr int NV = 4, NA = 20, NQ = 27, L1 = 2, BOUNDARY = 0, LINEAR = 1, NW = 0, NCW = 0, NC = 0, HAS_RES = 0, HAS_K = 1, TPB = 160, NSD = 4, KS = 4, ND = 256, NTC = 10, CG = 2, W = 5, LPW = 32, SMEM = 78256, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 4;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {0, 1, 2, 3}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {0, 1, 2, 3}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {0, 1, 2, 3}; return t[i]; }
@@ -46,7 +46,7 @@ struct F_b0_lin {
 extern "C" __global__ void __launch_bounds__(160, 2) mfb_b0_lin(const MfbArgs A) { mfb::assemble<F_b0_lin>(A); }
 
 struct F_b0_nl {
-  static constexpr int NV = 4, NA = 20, NQ = 27, L1 = 2, BOUNDARY = 0, LINEAR = 0, NW = 17, NCW = 0, NC = 0, HAS_RES = 1, HAS_K = 0, TPB = 160, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 29312, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 4;
+  static constexpr int NV = 4, NA = 20, NQ = 27, L1 = 2, BOUNDARY = 0, LINEAR = 0, NW = 17, NCW = 0, NC = 0, HAS_RES = 1, HAS_K = 0, TPB = 160, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 29232, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 4;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {0, 1, 2, 3}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {0, 1, 2, 3}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {0}; return t[i]; }
@@ -99,7 +99,7 @@ struct F_b0_nl {
 extern "C" __global__ void __launch_bounds__(160, 2) mfb_b0_nl(const MfbArgs A) { mfb::assemble<F_b0_nl>(A); }
 
 struct F_b1_lin {
-  static constexpr int NV = 4, NA = 20, NQ = 9, L1 = 2, BOUNDARY = 1, LINEAR = 1, NW = 0, NCW = 0, NC = 0, HAS_RES = 0, HAS_K = 1, TPB = 160, NSD = 1, KS = 1, ND = 16, NTC = 10, CG = 2, W = 5, LPW = 32, SMEM = 55168, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
+  static constexpr int NV = 4, NA = 20, NQ = 9, L1 = 2, BOUNDARY = 1, LINEAR = 1, NW = 0, NCW = 0, NC = 0, HAS_RES = 0, HAS_K = 1, TPB = 160, NSD = 1, KS = 1, ND = 16, NTC = 10, CG = 2, W = 5, LPW = 32, SMEM = 55088, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {0, -1, -1, -1}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {0}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {0}; return t[i]; }
@@ -118,7 +118,7 @@ struct F_b1_lin {
 extern "C" __global__ void __launch_bounds__(160, 2) mfb_b1_lin(const MfbArgs A) { mfb::assemble<F_b1_lin>(A); }
 
 struct F_b1_nl {
-  static constexpr int NV = 4, NA = 20, NQ = 9, L1 = 2, BOUNDARY = 1, LINEAR = 0, NW = 3, NCW = 0, NC = 0, HAS_RES = 1, HAS_K = 0, TPB = 160, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 6848, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
+  static constexpr int NV = 4, NA = 20, NQ = 9, L1 = 2, BOUNDARY = 1, LINEAR = 0, NW = 3, NCW = 0, NC = 0, HAS_RES = 1, HAS_K = 0, TPB = 160, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 6768, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {0, -1, -1, -1}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {0}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {0}; return t[i]; }
@@ -140,7 +140,7 @@ struct F_b1_nl {
 extern "C" __global__ void __launch_bounds__(160, 2) mfb_b1_nl(const MfbArgs A) { mfb::assemble<F_b1_nl>(A); }
 
 struct F_b2_lin {
-  static constexpr int NV = 4, NA = 20, NQ = 9, L1 = 2, BOUNDARY = 1, LINEAR = 1, NW = 0, NCW = 1, NC = 1, HAS_RES = 0, HAS_K = 1, TPB = 160, NSD = 1, KS = 1, ND = 16, NTC = 10, CG = 2, W = 5, LPW = 32, SMEM = 55168, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
+  static constexpr int NV = 4, NA = 20, NQ = 9, L1 = 2, BOUNDARY = 1, LINEAR = 1, NW = 0, NCW = 1, NC = 1, HAS_RES = 0, HAS_K = 1, TPB = 160, NSD = 1, KS = 1, ND = 16, NTC = 10, CG = 2, W = 5, LPW = 32, SMEM = 55088, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {0, -1, -1, -1}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {0}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {0}; return t[i]; }
@@ -158,7 +158,7 @@ struct F_b2_lin {
 extern "C" __global__ void __launch_bounds__(160, 2) mfb_b2_lin(const MfbArgs A) { mfb::assemble<F_b2_lin>(A); }
 
 struct F_b2_nl {
-  static constexpr int NV = 4, NA = 20, NQ = 9, L1 = 2, BOUNDARY = 1, LINEAR = 0, NW = 1, NCW = 1, NC = 1, HAS_RES = 1, HAS_K = 0, TPB = 160, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 7136, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
+  static constexpr int NV = 4, NA = 20, NQ = 9, L1 = 2, BOUNDARY = 1, LINEAR = 0, NW = 1, NCW = 1, NC = 1, HAS_RES = 1, HAS_K = 0, TPB = 160, NSD = 0, KS = 0, ND = 0, NTC = 2, CG = 1, W = 1, LPW = 1, SMEM = 7056, EVAL = 0, NQPI = 0, NQPO = 0, NGS = 1;
   __device__ static constexpr int gslot(int i) { constexpr int t[] = {0, -1, -1, -1}; return t[i]; }
   __device__ static constexpr int gslot_id(int i) { constexpr int t[] = {0}; return t[i]; }
   __device__ static constexpr int dslot(int i) { constexpr int t[] = {0}; return t[i]; }
