@@ -44,6 +44,7 @@ def parse():
                                                                 "(prints timings of the assembly only; never a bench value)")
     p.add_argument("--workload", default="neo_hookean", choices=list(WORKLOADS),
                    help="development aid: run another BASELINE config as the main workload (the driver's line is configs[2])")
+    p.add_argument("--ilu-only", action="store_true", help="development aid: one step, then the same system solved with Pl_ILU")
     p.add_argument("--spmv-sweep", action="store_true", help="development aid: time the SpMV tuning variants on the assembled "
                                                              "matrix and exit")
     p.add_argument("--detail-timers", action="store_true", help="time every Krylov reduction group and interface exchange inside the "
@@ -425,14 +426,21 @@ class Case:
         L, s = self.env.L, WORKLOADS[self.name]["solver"]
         defect, levels = C.c_double(0.0), C.c_int32(0)
         self.fd.ctx.call("mfb_ilu_selftest", C.byref(defect), C.byref(levels), None, 0)
-        info = L.SolveInfo()
+        info, info1 = L.SolveInfo(), L.SolveInfo()
+        # factorisation + one outer iteration (2 s products): what a solve costs before it iterates
+        ms1 = self.time_call(lambda: self.fd.ctx.call("mfb_krylov_solve_ex", L.MFB_BICGSTABL_GS, s["s"], 1, 1,
+                                                      WORKLOADS[self.name]["tol"], 1234, L.PR_JACOBI, L.PL_ILU, 200, None, C.byref(info1)))
+        self.profile(1)
+        self.profile_get()
         ms = self.time_call(lambda: self.fd.ctx.call("mfb_krylov_solve_ex", L.MFB_BICGSTABL_GS, s["s"], s["maxiter"], s["max_pass"],
                                                      WORKLOADS[self.name]["tol"], 1234, L.PR_JACOBI, L.PL_ILU, 200, None, C.byref(info)))
-        return {"solver": f"bicgstabl_GS s={s['s']}, right Jacobi + left Pl_ILU (block ILU(0), hash elimination order)",
+        pms, pcnt = self.profile_get()
+        return {"factorisation_plus_first_iteration_ms": ms1, "first_iteration_products": int(info1.spmv_count),
+                "sweeps_ms_per_product": pms[7] / max(pcnt[7], 1), "spmv_ms": pms[0] / max(pcnt[0], 1), "applications": int(pcnt[7]),"solver": f"bicgstabl_GS s={s['s']}, right Jacobi + left Pl_ILU (block ILU(0), elimination by colour classes)",
                 "solve_ms": ms, "krylov_iterations": int(info.iterations), "spmv_count": int(info.spmv_count), "passes": int(info.passes),
                 "converged": bool(info.converged), "final_residual": info.residual, "dependency_levels": int(levels.value),
                 "factorisation_defect_rel": defect.value,
-                "note": "solve_ms includes the factorisation; every product is followed by 2 x dependency_levels sweep launches"}
+                "note": "solve_ms includes the factorisation; every product is followed by 2 x dependency_levels - 1 sweep launches"}
 
     def profile(self, level):
         self.fd.ctx.call("mfb_profile_enable", level)
@@ -620,6 +628,13 @@ def main():
                 if rnd == 0:
                     out[v].append(f"maxdiff={diff.value:.2e}")
         print(json.dumps({"spmv_sweep_ms": out, "workload": name, "box": n}))
+        return
+    if args.ilu_only:
+        with torch.cuda.stream(env.stream):
+            case.step(False, True)
+        torch.cuda.synchronize()
+        out = [case.ilu_solve() for _ in range(2)]
+        print(json.dumps({"ilu_only": out, "order": os.environ.get("MFB_ILU_ORDER", "color"), "sweep": os.environ.get("MFB_ILU_SWEEP", "stream"), "rw": os.environ.get("MFB_ILU_RW", "8"), "workload": name, "box": n}))
         return
     if args.assembly_only:
         r = measure(case, K, W, e2e=False, solve=False)

@@ -14,8 +14,10 @@
 //                         upper part of row k (positions found by binary search in row i); then the inverse of U_ii
 //   apply  (per product)  forward sweep over the levels (unit L), backward sweep (U with the stored inverses), in place
 // Everything a row receives is written by its own warp: the factorisation and the sweeps are bit-reproducible.
+#include <cstdio>
 #include <thrust/device_ptr.h>
 #include <thrust/execution_policy.h>
+#include <thrust/scan.h>
 #include <thrust/sequence.h>
 #include <thrust/sort.h>
 
@@ -35,6 +37,31 @@ __device__ __forceinline__ u64 mix64(u64 z) {
 __global__ void k_prio(u64* key, int64_t N, const long long* gid) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < N) key[i] = mix64((u64)gid[i] + 0x5bd1e995ull);      // hash of the GLOBAL node id: the order does not depend on the internal numbering
+}
+// one relaxation round of the greedy colouring in priority order: colour[i] = smallest colour that no neighbour of HIGHER priority
+// carries (fixed point = the sequential greedy colouring by descending priority; reached after as many rounds as the priority
+// order has dependency levels). At most 128 colours (the node graph's degree bound is 81).
+__global__ void k_color_round(const int* nodeptr, const int* nodecol, const u64* key, int64_t N, const int* cin, int* cout, int* changed) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const u64 ki = key[i];
+    u64 m0 = 0, m1 = 0;
+    for (int p = nodeptr[i]; p < nodeptr[i + 1]; ++p) {
+        const int j = nodecol[p];
+        if (j == (int)i) continue;
+        const u64 kj = key[j];
+        if (kj > ki || (kj == ki && j > (int)i)) {
+            const int c = cin[j];
+            if (c < 64) m0 |= 1ull << c; else m1 |= 1ull << (c - 64 < 63 ? c - 64 : 63);
+        }
+    }
+    const int c = ~m0 ? __ffsll((long long)~m0) - 1 : 64 + __ffsll((long long)~m1) - 1;
+    cout[i] = c;
+    if (c != cin[i]) *changed = 1;
+}
+__global__ void k_color_key(u64* key, const int* color, int64_t N) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < N) key[i] = ((u64)color[i] << 56) | (key[i] >> 8);
 }
 __global__ void k_invert_perm(const int* order, int64_t N, int* pos) {
     int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -212,6 +239,83 @@ __global__ void __launch_bounds__(256) k_ilu_sweep(const int* __restrict__ rows,
     }
 }
 
+// ---- packed sweeps ----
+__global__ void k_pack_counts(const int* rows, const int* nodeptr, const int* nlow, int64_t N, int* cl, int* cu) {
+    int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (w >= N) return;
+    const int i = rows[w];
+    cl[w] = nlow[i];
+    cu[w] = nodeptr[i + 1] - nodeptr[i] - nlow[i] - 1;
+}
+__global__ void k_pack_index(const int* rows, const int* nodeptr, const int* nodecol, const unsigned char* kind, const int* lperm,
+                             const int* nlow, const int* Lptr, const int* Uptr, int64_t N, int* Lcol, int* Lsrc, int* Ucol, int* Usrc) {
+    int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (w >= N) return;
+    const int i = rows[w];
+    const int s = nodeptr[i], t = nodeptr[i + 1];
+    for (int q = 0; q < nlow[i]; ++q) { const int p = lperm[s + q]; Lcol[Lptr[w] + q] = nodecol[p]; Lsrc[Lptr[w] + q] = p; }
+    int u = Uptr[w];
+    for (int p = s; p < t; ++p)
+        if (kind[p] == 2) { Ucol[u] = nodecol[p]; Usrc[u] = p; ++u; }
+}
+template <typename VT>
+__global__ void k_pack_values(const int* src, int64_t n, int B, const double* F, VT* out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n * B) return;
+    out[t] = (VT)__ldcg(F + (size_t)src[t / B] * B + t % B);
+}
+// one level of a sweep on the packed factors: one warp per row, lane <-> fixed block position (i, k) like the SpMV, the row's
+// entries as one coalesced stream. LOWER: v_i -= sum L_ik v_k;  else v_i = U_ii^-1 (v_i - sum U_ij v_j)
+template <int NV, bool LOWER>
+__global__ void __launch_bounds__(256) k_ilu_sweep_packed(const int* __restrict__ rows, int w0, int n_rows, const int* __restrict__ ptr,
+                                                          const int* __restrict__ col, const double* __restrict__ val,
+                                                          const double* __restrict__ dinv, double* v) {
+    constexpr int B = NV * NV, EPW = 32 / B, ACTIVE = EPW * B;
+    const int wl = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (wl >= n_rows) return;
+    const int w = w0 + wl;
+    const int row = rows[w];
+    const int le = lane / B, ik = lane - le * B, i = ik / NV, k = ik - i * NV;
+    const bool on = lane < ACTIVE;
+    const int s = ptr[w], deg = on ? ptr[w + 1] - s : 0;
+    const double* Vp = val + (size_t)s * B + lane;
+    const int* Cp = col + s + le;
+    double a0 = 0.0, a1 = 0.0;
+    int e = le;
+    for (; e + EPW < deg; e += 2 * EPW) {
+        const double v0 = __ldcs(Vp + (size_t)(e - le) * B), v1 = __ldcs(Vp + (size_t)(e - le + EPW) * B);
+        const int c0 = __ldg(Cp + (e - le)), c1 = __ldg(Cp + (e - le + EPW));
+        a0 += v0 * __ldcg(v + (size_t)c0 * NV + k);
+        a1 += v1 * __ldcg(v + (size_t)c1 * NV + k);
+    }
+    if (e < deg) a0 += __ldcs(Vp + (size_t)(e - le) * B) * __ldcg(v + (size_t)__ldg(Cp + (e - le)) * NV + k);
+    const double acc = a0 + a1;
+    double t = acc;
+#pragma unroll
+    for (int d = 1; d < NV; ++d) t += __shfl_down_sync(0xffffffffu, acc, d);                 // sum over k
+    double r = t;
+    if constexpr ((B & (B - 1)) == 0) {
+#pragma unroll
+        for (int o = 16; o >= B; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    } else {
+#pragma unroll
+        for (int d = 1; d < EPW; ++d) r += __shfl_down_sync(0xffffffffu, t, d * B);          // sum over the EPW entries
+    }
+    // lanes ik = i * NV (le == 0, k == 0) hold component i of the row's sum
+    const double yi = (le == 0 && k == 0 && on) ? v[(size_t)row * NV + i] - r : 0.0;
+    if (LOWER) {
+        if (le == 0 && k == 0 && on) v[(size_t)row * NV + i] = yi;
+    } else {
+        double z = 0.0;                                                                        // z_i = sum_m dinv[i][m] y_m
+#pragma unroll
+        for (int m = 0; m < NV; ++m) {
+            const double ym = __shfl_sync(0xffffffffu, yi, m * NV);
+            if (le == 0 && k == 0 && on) z += __ldg(dinv + (size_t)row * B + i * NV + m) * ym;
+        }
+        if (le == 0 && k == 0 && on) v[(size_t)row * NV + i] = z;
+    }
+}
+
 // defect of the defining property (L U)_ij = A_ij on the pattern: one warp per row, max |.| into out[0], max |A| into out[1]
 template <int NV>
 __global__ void __launch_bounds__(256) k_ilu_defect(const int* __restrict__ nodeptr, const int* __restrict__ nodecol,
@@ -286,6 +390,13 @@ struct IluPlan {
     DevBuf<unsigned char> kind;
     std::vector<int> level_ptr;          // rows of level l: rows[level_ptr[l] .. level_ptr[l+1])
     DevBuf<double> F, dinv;              // factors in the matrix's block layout, inverted diagonal blocks
+    // packed factors for the sweeps: rows in LEVEL order, the lower (upper) entries of a row contiguous, so that a sweep level is one
+    // contiguous range of rows and entries read as a coalesced stream (the layout of the matrix interleaves lower and upper entries)
+    DevBuf<int> Lptr, Uptr, Lcol, Ucol, Lsrc, Usrc;   // [N+1], [N+1], [UL], [UU], source position of every packed entry in F
+    DevBuf<double> Lval, Uval;
+    DevBuf<float> Lval32, Uval32;        // the packed factors rounded to FP32 (default for the sweeps, see ilu_use_f32)
+    bool f32 = false;
+    int64_t UL = 0, UU = 0;
     bool factored = false;
 };
 static std::map<mfb_ctx*, IluPlan*>& ilu_table() {
@@ -309,6 +420,26 @@ static int ilu_setup(mfb_ctx* ctx, IluPlan*& P) {
     DevBuf<int> order, lev2, changed;
     MFB_CUDA(key.alloc(N)); MFB_CUDA(order.alloc(N)); MFB_CUDA(P->pos.alloc(N));
     LAUNCH(k_prio, nblk(N), TPB, key.p, N, ctx->gid.p);
+    // elimination by colour classes of a greedy colouring (ties inside a class by the hash): the dependency levels are bounded by
+    // the number of colours (32 at 88^3) instead of the depth of the plain hash order (127; MFB_ILU_ORDER=hash, round-2 first version)
+    static const bool by_color = [] { const char* e = getenv("MFB_ILU_ORDER"); return !(e && e[0] == 'h'); }();
+    if (by_color) {
+        DevBuf<int> ca, cb, chg;
+        MFB_CUDA(ca.alloc(N)); MFB_CUDA(cb.alloc(N)); MFB_CUDA(chg.alloc(1));
+        MFB_CUDA(cudaMemsetAsync(ca.p, 0, N * sizeof(int), ctx->stream));
+        int *a = ca.p, *b = cb.p;
+        for (int round = 0; round < 100000; ++round) {
+            MFB_CUDA(cudaMemsetAsync(chg.p, 0, sizeof(int), ctx->stream));
+            LAUNCH(k_color_round, nblk(N), TPB, ctx->nodeptr.p, ctx->nodecol.p, key.p, N, a, b, chg.p);
+            int h = 0;
+            MFB_CUDA(cudaMemcpyAsync(&h, chg.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+            std::swap(a, b);
+            if (!h) break;
+        }
+        LAUNCH(k_color_key, nblk(N), TPB, key.p, a, N);
+        MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     thrust::device_ptr<int> op(order.p);
     thrust::device_ptr<u64> kp(key.p);
     thrust::sequence(pol, op, op + N);
@@ -343,8 +474,32 @@ static int ilu_setup(mfb_ctx* ctx, IluPlan*& P) {
     P->level_ptr.assign(n_levels + 1, 0);
     for (int64_t r = 0; r < N; ++r) P->level_ptr[hl[r] + 1]++;
     for (int l = 0; l < n_levels; ++l) P->level_ptr[l + 1] += P->level_ptr[l];
+    if (getenv("MFB_ILU_VERBOSE")) {
+        fprintf(stderr, "[mfb ilu] %d levels, rows per level:", n_levels);
+        for (int l = 0; l < n_levels; ++l) fprintf(stderr, " %d", P->level_ptr[l + 1] - P->level_ptr[l]);
+        fprintf(stderr, "\n");
+    }
     MFB_CUDA(P->lperm.alloc(U)); MFB_CUDA(P->nlow.alloc(N));
     LAUNCH(k_lower_order, nblk(N), TPB, ctx->nodeptr.p, ctx->nodecol.p, P->kind.p, P->pos.p, N, P->lperm.p, P->nlow.p);
+    // packed layout of the sweeps: rows in level order, lower / upper entries contiguous
+    MFB_CUDA(P->Lptr.alloc(N + 1)); MFB_CUDA(P->Uptr.alloc(N + 1));
+    MFB_CUDA(cudaMemsetAsync(P->Lptr.p, 0, (N + 1) * sizeof(int), ctx->stream));
+    MFB_CUDA(cudaMemsetAsync(P->Uptr.p, 0, (N + 1) * sizeof(int), ctx->stream));
+    LAUNCH(k_pack_counts, nblk(N), TPB, P->rows.p, ctx->nodeptr.p, P->nlow.p, N, P->Lptr.p, P->Uptr.p);
+    {
+        thrust::device_ptr<int> a(P->Lptr.p), b(P->Uptr.p);
+        thrust::exclusive_scan(pol, a, a + (N + 1), a);
+        thrust::exclusive_scan(pol, b, b + (N + 1), b);
+        int ul = 0, uu = 0;
+        MFB_CUDA(cudaMemcpyAsync(&ul, P->Lptr.p + N, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        MFB_CUDA(cudaMemcpyAsync(&uu, P->Uptr.p + N, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        MFB_CUDA(cudaStreamSynchronize(ctx->stream));
+        P->UL = ul; P->UU = uu;
+    }
+    MFB_CUDA(P->Lcol.alloc(P->UL + MFB_STREAM_PAD)); MFB_CUDA(P->Lsrc.alloc(P->UL > 0 ? P->UL : 1));
+    MFB_CUDA(P->Ucol.alloc(P->UU + MFB_STREAM_PAD)); MFB_CUDA(P->Usrc.alloc(P->UU > 0 ? P->UU : 1));
+    LAUNCH(k_pack_index, nblk(N), TPB, P->rows.p, ctx->nodeptr.p, ctx->nodecol.p, P->kind.p, P->lperm.p, P->nlow.p, P->Lptr.p, P->Uptr.p, N,
+           P->Lcol.p, P->Lsrc.p, P->Ucol.p, P->Usrc.p);
     MFB_CUDA(cudaStreamSynchronize(ctx->stream));
     MFB_CUDA(cudaGetLastError());
     return MFB_OK;
@@ -360,20 +515,44 @@ static int ilu_factor_nv(mfb_ctx* ctx, IluPlan* P) {
     }
     return MFB_OK;
 }
+static bool ilu_stream_sweeps() {
+    static const bool on = [] { const char* e = getenv("MFB_ILU_SWEEP"); return !(e && e[0] == 'r'); }();   // "row": one warp per row
+    return on;
+}
+// The packed factors are kept in FP32 (accumulation in FP64): the incomplete factorisation is an approximation of A to a few
+// per cent, rounding its entries to 2^-24 does not change what it does to the spectrum, and the sweeps -- pure streaming of the
+// factors -- move half the bytes. The preconditioner stays one fixed linear operator, so the Krylov methods converge to the same
+// tolerance on the TRUE residual (which never sees the factors). MFB_ILU_FP64=1 keeps doubles.
+static bool ilu_use_f32(mfb_ctx* ctx) {
+    static const bool f64 = [] { const char* e = getenv("MFB_ILU_FP64"); return e && e[0] == '1'; }();
+    static const bool unpacked = [] { const char* e = getenv("MFB_ILU_UNPACKED"); return e && e[0] == '1'; }();
+    return !f64 && !unpacked && ilu_stream_sweeps() && ctx->n_var <= 4;
+}
+
 template <int NV>
 static int ilu_apply_nv(mfb_ctx* ctx, IluPlan* P, double* v) {
     const int nl = (int)P->level_ptr.size() - 1;
-    for (int l = 0; l < nl; ++l) {
+    static const bool unpacked = [] { const char* e = getenv("MFB_ILU_UNPACKED"); return e && e[0] == '1'; }();   // round-2 first version (A/B)
+    const bool stream_kernel = ilu_stream_sweeps();
+    for (int l = 1; l < nl; ++l) {                               // level 0 has no lower entries
         const int off = P->level_ptr[l], cnt = P->level_ptr[l + 1] - off;
-        if (cnt > 0 && l > 0)                                    // level 0 has no lower entries
+        if (cnt <= 0) continue;
+        if (unpacked)
             LAUNCH((k_ilu_sweep<NV, true>), nblk((int64_t)cnt * 32), TPB, P->rows.p + off, cnt, ctx->nodeptr.p, ctx->nodecol.p, P->kind.p, P->F.p,
                    P->dinv.p, v);
+        else if (!(stream_kernel && mfb_sweep_level_mr(ctx, false, P->Lptr.p, P->Lcol.p, P->f32 ? (const void*)P->Lval32.p : (const void*)P->Lval.p,
+                                                       P->f32, P->rows.p, P->dinv.p, v, off, off + cnt)))
+            LAUNCH((k_ilu_sweep_packed<NV, true>), nblk((int64_t)cnt * 32), TPB, P->rows.p, off, cnt, P->Lptr.p, P->Lcol.p, P->Lval.p, P->dinv.p, v);
     }
     for (int l = nl - 1; l >= 0; --l) {
         const int off = P->level_ptr[l], cnt = P->level_ptr[l + 1] - off;
-        if (cnt > 0)
+        if (cnt <= 0) continue;
+        if (unpacked)
             LAUNCH((k_ilu_sweep<NV, false>), nblk((int64_t)cnt * 32), TPB, P->rows.p + off, cnt, ctx->nodeptr.p, ctx->nodecol.p, P->kind.p, P->F.p,
                    P->dinv.p, v);
+        else if (!(stream_kernel && mfb_sweep_level_mr(ctx, true, P->Uptr.p, P->Ucol.p, P->f32 ? (const void*)P->Uval32.p : (const void*)P->Uval.p,
+                                                       P->f32, P->rows.p, P->dinv.p, v, off, off + cnt)))
+            LAUNCH((k_ilu_sweep_packed<NV, false>), nblk((int64_t)cnt * 32), TPB, P->rows.p, off, cnt, P->Uptr.p, P->Ucol.p, P->Uval.p, P->dinv.p, v);
     }
     return MFB_OK;
 }
@@ -394,6 +573,16 @@ int mfb_ilu_factor(mfb_ctx* ctx, const double* A, int* n_levels) {
         case 3: MFB_TRY(ilu_factor_nv<3>(ctx, P)); break;
         default: MFB_TRY(ilu_factor_nv<4>(ctx, P)); break;
     }
+    P->f32 = ilu_use_f32(ctx);
+    if (P->f32) {
+        MFB_CUDA(P->Lval32.alloc((size_t)(P->UL + MFB_STREAM_PAD) * B)); MFB_CUDA(P->Uval32.alloc((size_t)(P->UU + MFB_STREAM_PAD) * B));
+        if (P->UL > 0) LAUNCH(k_pack_values<float>, nblk(P->UL * B), TPB, P->Lsrc.p, P->UL, B, P->F.p, P->Lval32.p);
+        if (P->UU > 0) LAUNCH(k_pack_values<float>, nblk(P->UU * B), TPB, P->Usrc.p, P->UU, B, P->F.p, P->Uval32.p);
+    } else {
+        MFB_CUDA(P->Lval.alloc((size_t)(P->UL + MFB_STREAM_PAD) * B)); MFB_CUDA(P->Uval.alloc((size_t)(P->UU + MFB_STREAM_PAD) * B));
+        if (P->UL > 0) LAUNCH(k_pack_values<double>, nblk(P->UL * B), TPB, P->Lsrc.p, P->UL, B, P->F.p, P->Lval.p);
+        if (P->UU > 0) LAUNCH(k_pack_values<double>, nblk(P->UU * B), TPB, P->Usrc.p, P->UU, B, P->F.p, P->Uval.p);
+    }
     MFB_CUDA(cudaGetLastError());
     P->factored = true;
     if (n_levels) *n_levels = (int)P->level_ptr.size() - 1;
@@ -405,6 +594,7 @@ int mfb_ilu_apply(mfb_ctx* ctx, double* v) {
     auto it = ilu_table().find(ctx);
     MFB_REQUIRE(it != ilu_table().end() && it->second->factored, MFB_ERR_STATE, "Pl_ILU applied before it was factorised");
     IluPlan* P = it->second;
+    ProfScope ps(ctx, MFB_T_PRECOND);
     switch (ctx->n_var) {
         case 1: MFB_TRY(ilu_apply_nv<1>(ctx, P, v)); break;
         case 2: MFB_TRY(ilu_apply_nv<2>(ctx, P, v)); break;

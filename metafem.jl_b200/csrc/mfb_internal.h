@@ -87,7 +87,7 @@ struct MeshBuild;  // mfb_meshbuild.cu
 
 // CUDA-event timers on the context's stream (bench.py roofline numbers); ids = MFB_T_*
 enum { MFB_T_SPMV = 0, MFB_T_ASM_NONLINEAR = 1, MFB_T_ASM_LINEAR = 2, MFB_T_SOLVE = 3, MFB_T_ELEM_KERNEL = 4, MFB_T_HALO = 5,
-       MFB_T_REDUCE = 6, MFB_T_COUNT = 8 };
+       MFB_T_REDUCE = 6, MFB_T_PRECOND = 7, MFB_T_COUNT = 8 };
 struct ProfEvents {
     std::vector<cudaEvent_t> start, stop;
 };
@@ -277,4 +277,6 @@ int mfb_qp_lookup(mfb_ctx* ctx, const std::string& name, double** p);   // creat
 // mfb_krylov.cu
 int mfb_spmv_internal(mfb_ctx* ctx, const double* K, const double* x, double* y);
 int mfb_spmv_kind(mfb_ctx* ctx);   // 0 = one warp per row (k_spmv_bsr), 1 = multi-row streams (k_spmv_mr)
+bool mfb_sweep_level_mr(mfb_ctx* ctx, bool upper, const int* ptr, const int* col, const void* val, bool f32, const int* rowid,
+                        const double* dinv, double* v, int w0, int w1);
 int mfb_spmv_t_internal(mfb_ctx* ctx, const double* K, const double* x, double* y);   // y = K' x

@@ -850,6 +850,7 @@ template <int LDK> __device__ __forceinline__ double ld_stream_f64(const double*
     asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
+template <int LDK> __device__ __forceinline__ double ld_stream_f64(const float* p) { return (double)__ldcs(p); }   // FP32-stored factors
 template <int LDK> __device__ __forceinline__ int ld_stream_s32(const int* p) {
     if constexpr (LDK == 0) return __ldg(p);
     int v;
@@ -864,9 +865,12 @@ template <int LDK> __device__ __forceinline__ double ld_gather_f64(const double*
 }
 
 // the stream loop of one warp (its RW consecutive rows)
-template <int NV, int UNR, int RW, int LDK>
-__device__ __forceinline__ void spmv_mr_rows(const int* __restrict__ nodeptr, const int* __restrict__ nodecol, const double* __restrict__ K,
-                                          const double* __restrict__ x, double* __restrict__ y, int64_t N, int64_t row0) {
+// OUT = 0: y[row] = sum (the product). OUT = 1 / 2: one level of a triangular sweep on packed factors (mfb_ilu.cu): the "rows" are
+// positions in level order, rowid[] their node ids, x == y == v:  v[id] -= sum  /  v[id] = dinv[id] (v[id] - sum)
+template <int NV, int UNR, int RW, int LDK, int OUT = 0, typename VT = double>
+__device__ __forceinline__ void spmv_mr_rows(const int* __restrict__ nodeptr, const int* __restrict__ nodecol, const VT* __restrict__ K,
+                                          const double* x, double* y, int64_t N, int64_t row0,
+                                          const int* __restrict__ rowid = nullptr, const double* __restrict__ dinv = nullptr) {
     static_assert(RW <= 31, "lane l holds the row pointer of row l: at most 31 rows per warp");
     constexpr int B = NV * NV, EPW = 32 / B, ACTIVE = EPW * B, W = UNR * EPW;
     constexpr unsigned FULL = 0xffffffffu;
@@ -876,11 +880,26 @@ __device__ __forceinline__ void spmv_mr_rows(const int* __restrict__ nodeptr, co
     const double* xk = x + k;
     const int nr = (int)min((int64_t)RW, N - row0);
     const int myp = (lane <= nr) ? __ldg(nodeptr + row0 + lane) : 0;     // lane l holds nodeptr[row0 + l]
+    // sweeps: the row's own entries of v (and its inverse diagonal block) are fetched now, while the stream runs -- a load at the
+    // row end would stall the warp once per (short) row. Lane q < nr * NV holds component q % NV of row q / NV.
+    int myid = 0;
+    double myv = 0.0, myd[OUT == 2 ? NV : 1];
+    if constexpr (OUT != 0) {
+        static_assert(OUT == 0 || RW * NV <= 32, "own entries of the warp's rows are held one per lane");
+        myid = (lane < nr) ? __ldg(rowid + row0 + lane) : 0;
+        const int idq = __shfl_sync(FULL, myid, (lane / NV) & 31);
+        const bool has = lane < nr * NV;
+        myv = has ? y[(size_t)idq * NV + lane % NV] : 0.0;
+        if constexpr (OUT == 2) {
+#pragma unroll
+            for (int m = 0; m < NV; ++m) myd[m] = has ? __ldg(dinv + (size_t)idq * B + (lane % NV) * NV + m) : 0.0;
+        }
+    }
     const int s = __shfl_sync(FULL, myp, 0);
     const int degw = __shfl_sync(FULL, myp, nr) - s;                     // length of the whole stream (warp-uniform)
     const int deg = on ? degw : 0;
     int cr = 0, lo = 0, hi = __shfl_sync(FULL, myp, 1) - s;              // current row and its entry range within the stream
-    const double* Kp = K + (size_t)s * B + lane;
+    const VT* Kp = K + (size_t)s * B + lane;
     const int* Cp = nodecol + s + le;
     double a[UNR], v[UNR];
     int c[UNR];
@@ -934,7 +953,22 @@ __device__ __forceinline__ void spmv_mr_rows(const int* __restrict__ nodeptr, co
 #pragma unroll
                     for (int d = 1; d < EPW; ++d) r += __shfl_down_sync(FULL, t, d * B);    // sum over the EPW entries
                 }
-                if (le == 0 && k == 0 && on) y[(size_t)(row0 + cr) * NV + i] = r;
+                if constexpr (OUT == 0) {
+                    if (le == 0 && k == 0 && on) y[(size_t)(row0 + cr) * NV + i] = r;
+                } else {
+                    const int id = __shfl_sync(FULL, myid, cr);
+                    const bool wr = le == 0 && k == 0 && on;
+                    const int src = (cr * NV + i) & 31;
+                    const double yi = __shfl_sync(FULL, myv, src) - r;
+                    if constexpr (OUT == 1) {
+                        if (wr) y[(size_t)id * NV + i] = yi;
+                    } else {
+                        double z = 0.0;
+#pragma unroll
+                        for (int m = 0; m < NV; ++m) z = fma(__shfl_sync(FULL, myd[m], src), __shfl_sync(FULL, yi, m * NV), z);
+                        if (wr) y[(size_t)id * NV + i] = z;
+                    }
+                }
                 ++cr;
                 lo = hi;
                 if (cr >= nr) break;
@@ -1351,7 +1385,49 @@ void launch_spmv_mr(mfb_ctx* ctx, const double* K, const double* x, double* y, c
     else k_spmv_mr<NV, SpmvUnroll<NV>::value, RW, false, MINB><<<grid, 256, 0, ctx->stream>>>(ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N, w, R.sc, R.red, R.partials, R.counter, op.op);
     ctx->launches++;
 }
+template <int NV, int UNR, int RW, int OUT, int MINB, typename VT>
+__global__ void __launch_bounds__(256, MINB) k_sweep_mr(const int* __restrict__ ptr, const int* __restrict__ col, const VT* __restrict__ val,
+                                                        double* v, int w0, int w1, const int* __restrict__ rowid, const double* __restrict__ dinv) {
+    const int64_t row0 = w0 + (blockIdx.x * (int64_t)8 + (threadIdx.x >> 5)) * RW;
+    if (row0 < w1) spmv_mr_rows<NV, UNR, RW, 0, OUT, VT>(ptr, col, val, v, v, (int64_t)w1, row0, rowid, dinv);
+}
+template <int NV, int RW, int UNR, int MINB>
+void launch_sweep_mr(mfb_ctx* ctx, bool upper, const int* ptr, const int* col, const void* val, bool f32, const int* rowid, const double* dinv,
+                     double* v, int w0, int w1) {
+    const unsigned grid = (unsigned)((w1 - w0 + 8 * RW - 1) / (8 * RW));
+    const float* vf = static_cast<const float*>(val);
+    const double* vd = static_cast<const double*>(val);
+    if (f32) {
+        if (upper) k_sweep_mr<NV, UNR, RW, 2, MINB, float><<<grid, 256, 0, ctx->stream>>>(ptr, col, vf, v, w0, w1, rowid, dinv);
+        else k_sweep_mr<NV, UNR, RW, 1, MINB, float><<<grid, 256, 0, ctx->stream>>>(ptr, col, vf, v, w0, w1, rowid, dinv);
+    } else {
+        if (upper) k_sweep_mr<NV, UNR, RW, 2, MINB, double><<<grid, 256, 0, ctx->stream>>>(ptr, col, vd, v, w0, w1, rowid, dinv);
+        else k_sweep_mr<NV, UNR, RW, 1, MINB, double><<<grid, 256, 0, ctx->stream>>>(ptr, col, vd, v, w0, w1, rowid, dinv);
+    }
+    ctx->launches++;
+}
 }  // namespace
+
+// one level [w0, w1) of a triangular sweep on the packed factors of mfb_ilu.cu with the multi-row stream kernel of the SpMV
+// (the level's rows are contiguous in the packed arrays and independent of one another); `val` holds doubles or floats.
+// false: n_var without this kernel.
+bool mfb_sweep_level_mr(mfb_ctx* ctx, bool upper, const int* ptr, const int* col, const void* val, bool f32, const int* rowid,
+                        const double* dinv, double* v, int w0, int w1) {
+    static const int cfg = [] { const char* e = getenv("MFB_ILU_CFG"); return e ? atoi(e) : 0; }();   // tuning aid
+    switch (ctx->n_var) {
+        case 1: launch_sweep_mr<1, 8, 2, 4>(ctx, upper, ptr, col, val, f32, rowid, dinv, v, w0, w1); return true;
+        case 2: launch_sweep_mr<2, 8, 3, 4>(ctx, upper, ptr, col, val, f32, rowid, dinv, v, w0, w1); return true;
+        case 3:
+            switch (cfg) {
+                case 1: launch_sweep_mr<3, 8, 4, 4>(ctx, upper, ptr, col, val, f32, rowid, dinv, v, w0, w1); break;
+                case 2: launch_sweep_mr<3, 4, 4, 4>(ctx, upper, ptr, col, val, f32, rowid, dinv, v, w0, w1); break;
+                default: launch_sweep_mr<3, 8, 5, 3>(ctx, upper, ptr, col, val, f32, rowid, dinv, v, w0, w1); break;   // best of the variants measured (profiles/ilu_r2.md)
+            }
+            return true;
+        case 4: launch_sweep_mr<4, 8, 5, 3>(ctx, upper, ptr, col, val, f32, rowid, dinv, v, w0, w1); return true;
+        default: return false;
+    }
+}
 
 // y = K x (block rows of this rank). w != nullptr (multi-row kernel only): also red[0] = sum_rows w . y, folded and followed by
 // the scalar op in the kernel's tail; R.sc != nullptr: the launch is skipped on the device once the solver's stop flag is up.
