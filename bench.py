@@ -617,7 +617,7 @@ def main():
             case.step(False, False)
         out = {}
         for rnd in range(2):
-            for v in range(0, 32):
+            for v in ([int(x) for x in os.environ['MFB_SWEEP_VARIANTS'].split(',')] if os.environ.get('MFB_SWEEP_VARIANTS') else range(0, 32)):
                 ms, diff = C.c_double(0.0), C.c_double(0.0)
                 try:
                     fd.ctx.call("mfb_spmv_variant_bench", v, 20, C.byref(ms), C.byref(diff) if rnd == 0 else None)
@@ -690,7 +690,7 @@ def main():
                 "parallelism": plane, "krylov_iterations_per_step": r["krylov_iterations"], "spmv_per_step": r["spmv"],
                 "passes_max": r["passes_max"], "solver_converged": r["all_converged"], "initial_residual": r["initial_residual"],
                 "final_residual_max": r["final_residual_max"], "setup_s": case.setup_s,
-                "spmv_kernel": "k_spmv_mr (multi-row streams, dot fused into the tail)" if os.environ.get("MFB_SPMV", "mr")[0] not in "r0" else "k_spmv_bsr (one warp per row)",
+                "spmv_kernel": "k_spmv_mr (multi-row streams)" if os.environ.get("MFB_SPMV", "mr")[0] not in "r0" else "k_spmv_bsr (one warp per row)",
                 "dist_check": dc}),
             "newton_step_ms": r["ms_per_step"], "assembly_ms": r["assembly_ms"], "assembly_dof_per_s": r["assembly_dof_per_s"],
             "element_kernel_ms": r["element_kernel_ms"], "K_linear_ms": r["K_linear_ms"], "solve_ms": r["solve_ms"], "spmv_ms": r["spmv_ms"],

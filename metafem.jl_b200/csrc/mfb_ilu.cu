@@ -15,6 +15,7 @@
 //   apply  (per product)  forward sweep over the levels (unit L), backward sweep (U with the stored inverses), in place
 // Everything a row receives is written by its own warp: the factorisation and the sweeps are bit-reproducible.
 #include <cstdio>
+#include <cstring>
 #include <thrust/device_ptr.h>
 #include <thrust/execution_policy.h>
 #include <thrust/scan.h>
@@ -264,6 +265,25 @@ __global__ void k_pack_values(const int* src, int64_t n, int B, const double* F,
     if (t >= n * B) return;
     out[t] = (VT)__ldcg(F + (size_t)src[t / B] * B + t % B);
 }
+// packed upper entries of the stream-kernel sweeps: U'_ij = U_ii^-1 U_ij, so that the backward sweep is z_i = (U_ii^-1 y_i) - sum U'_ij z_j
+// and its row epilogue needs no block product (one warp per row)
+template <int NV, typename VT>
+__global__ void k_pack_upper_scaled(const int* __restrict__ rows, const int* __restrict__ ptr, const int* __restrict__ src, int64_t n_rows,
+                                    const double* __restrict__ F, const double* __restrict__ dinv, VT* __restrict__ out) {
+    constexpr int B = NV * NV;
+    const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_rows) return;
+    double d[B], a[B], c[B];
+    ld_block<NV>(dinv + (size_t)rows[w] * B, d);
+    for (int j = ptr[w] + lane; j < ptr[w + 1]; j += 32) {
+        ld_block<NV>(F + (size_t)src[j] * B, a);
+        mul_block<NV>(d, a, c);
+#pragma unroll
+        for (int q = 0; q < B; ++q) out[(size_t)j * B + q] = (VT)c[q];
+    }
+}
+
 // one level of a sweep on the packed factors: one warp per row, lane <-> fixed block position (i, k) like the SpMV, the row's
 // entries as one coalesced stream. LOWER: v_i -= sum L_ik v_k;  else v_i = U_ii^-1 (v_i - sum U_ij v_j)
 template <int NV, bool LOWER>
@@ -396,6 +416,7 @@ struct IluPlan {
     DevBuf<double> Lval, Uval;
     DevBuf<float> Lval32, Uval32;        // the packed factors rounded to FP32 (default for the sweeps, see ilu_use_f32)
     bool f32 = false;
+    bool scaledU = false;                // packed upper entries pre-multiplied by the inverse diagonal block of their row
     int64_t UL = 0, UU = 0;
     bool factored = false;
 };
@@ -523,17 +544,30 @@ static bool ilu_stream_sweeps() {
 // per cent, rounding its entries to 2^-24 does not change what it does to the spectrum, and the sweeps -- pure streaming of the
 // factors -- move half the bytes. The preconditioner stays one fixed linear operator, so the Krylov methods converge to the same
 // tolerance on the TRUE residual (which never sees the factors). MFB_ILU_FP64=1 keeps doubles.
+static bool ilu_unpacked() {
+    static const bool on = [] { const char* e = getenv("MFB_ILU_UNPACKED"); return e && e[0] == '1'; }();   // round-2 first version (A/B)
+    return on;
+}
 static bool ilu_use_f32(mfb_ctx* ctx) {
     static const bool f64 = [] { const char* e = getenv("MFB_ILU_FP64"); return e && e[0] == '1'; }();
-    static const bool unpacked = [] { const char* e = getenv("MFB_ILU_UNPACKED"); return e && e[0] == '1'; }();
-    return !f64 && !unpacked && ilu_stream_sweeps() && ctx->n_var <= 4;
+    return !f64 && !ilu_unpacked() && ilu_stream_sweeps() && ctx->n_var <= 4;
+}
+template <typename VT>
+static void pack_upper_scaled(mfb_ctx* ctx, IluPlan* P, VT* out) {
+    const unsigned grid = nblk(P->N * 32);
+    switch (ctx->n_var) {
+        case 1: LAUNCH((k_pack_upper_scaled<1, VT>), grid, TPB, P->rows.p, P->Uptr.p, P->Usrc.p, P->N, P->F.p, P->dinv.p, out); break;
+        case 2: LAUNCH((k_pack_upper_scaled<2, VT>), grid, TPB, P->rows.p, P->Uptr.p, P->Usrc.p, P->N, P->F.p, P->dinv.p, out); break;
+        case 3: LAUNCH((k_pack_upper_scaled<3, VT>), grid, TPB, P->rows.p, P->Uptr.p, P->Usrc.p, P->N, P->F.p, P->dinv.p, out); break;
+        default: LAUNCH((k_pack_upper_scaled<4, VT>), grid, TPB, P->rows.p, P->Uptr.p, P->Usrc.p, P->N, P->F.p, P->dinv.p, out); break;
+    }
 }
 
 template <int NV>
 static int ilu_apply_nv(mfb_ctx* ctx, IluPlan* P, double* v) {
     const int nl = (int)P->level_ptr.size() - 1;
-    static const bool unpacked = [] { const char* e = getenv("MFB_ILU_UNPACKED"); return e && e[0] == '1'; }();   // round-2 first version (A/B)
-    const bool stream_kernel = ilu_stream_sweeps();
+    const bool unpacked = ilu_unpacked();
+    const bool stream_kernel = P->scaledU;
     for (int l = 1; l < nl; ++l) {                               // level 0 has no lower entries
         const int off = P->level_ptr[l], cnt = P->level_ptr[l + 1] - off;
         if (cnt <= 0) continue;
@@ -574,14 +608,17 @@ int mfb_ilu_factor(mfb_ctx* ctx, const double* A, int* n_levels) {
         default: MFB_TRY(ilu_factor_nv<4>(ctx, P)); break;
     }
     P->f32 = ilu_use_f32(ctx);
+    P->scaledU = ilu_stream_sweeps() && ctx->n_var <= 4 && !ilu_unpacked();
     if (P->f32) {
         MFB_CUDA(P->Lval32.alloc((size_t)(P->UL + MFB_STREAM_PAD) * B)); MFB_CUDA(P->Uval32.alloc((size_t)(P->UU + MFB_STREAM_PAD) * B));
         if (P->UL > 0) LAUNCH(k_pack_values<float>, nblk(P->UL * B), TPB, P->Lsrc.p, P->UL, B, P->F.p, P->Lval32.p);
-        if (P->UU > 0) LAUNCH(k_pack_values<float>, nblk(P->UU * B), TPB, P->Usrc.p, P->UU, B, P->F.p, P->Uval32.p);
+        if (P->scaledU) pack_upper_scaled<float>(ctx, P, P->Uval32.p);
+        else if (P->UU > 0) LAUNCH(k_pack_values<float>, nblk(P->UU * B), TPB, P->Usrc.p, P->UU, B, P->F.p, P->Uval32.p);
     } else {
         MFB_CUDA(P->Lval.alloc((size_t)(P->UL + MFB_STREAM_PAD) * B)); MFB_CUDA(P->Uval.alloc((size_t)(P->UU + MFB_STREAM_PAD) * B));
         if (P->UL > 0) LAUNCH(k_pack_values<double>, nblk(P->UL * B), TPB, P->Lsrc.p, P->UL, B, P->F.p, P->Lval.p);
-        if (P->UU > 0) LAUNCH(k_pack_values<double>, nblk(P->UU * B), TPB, P->Usrc.p, P->UU, B, P->F.p, P->Uval.p);
+        if (P->scaledU) pack_upper_scaled<double>(ctx, P, P->Uval.p);
+        else if (P->UU > 0) LAUNCH(k_pack_values<double>, nblk(P->UU * B), TPB, P->Usrc.p, P->UU, B, P->F.p, P->Uval.p);
     }
     MFB_CUDA(cudaGetLastError());
     P->factored = true;
@@ -595,11 +632,41 @@ int mfb_ilu_apply(mfb_ctx* ctx, double* v) {
     MFB_REQUIRE(it != ilu_table().end() && it->second->factored, MFB_ERR_STATE, "Pl_ILU applied before it was factorised");
     IluPlan* P = it->second;
     ProfScope ps(ctx, MFB_T_PRECOND);
+    // experiment (MFB_ILU_L2WIN=1): the swept vector as a persisting access-policy window of the stream
+    static const bool win = [] { const char* e = getenv("MFB_ILU_L2WIN"); return e && e[0] == '1'; }();
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    if (win) {
+        static size_t max_win = 0;
+        if (!max_win) {
+            cudaDeviceProp prop;
+            MFB_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+            size_t aside = (size_t)prop.persistingL2CacheMaxSize;
+            const size_t want = (size_t)ctx->N * ctx->n_var * sizeof(double) * 5 / 4;
+            if (aside > want) aside = want;
+            MFB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, aside));
+            max_win = (size_t)prop.accessPolicyMaxWindowSize;
+            fprintf(stderr, "[mfb ilu] persisting L2 set-aside %zu MB (max %d MB), window max %zu MB\n", aside >> 20,
+                    prop.persistingL2CacheMaxSize >> 20, max_win >> 20);
+        }
+        size_t bytes = (size_t)ctx->N * ctx->n_var * sizeof(double);
+        if (bytes > max_win) bytes = max_win;
+        attr.accessPolicyWindow.base_ptr = v;
+        attr.accessPolicyWindow.num_bytes = bytes;
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        MFB_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    }
     switch (ctx->n_var) {
         case 1: MFB_TRY(ilu_apply_nv<1>(ctx, P, v)); break;
         case 2: MFB_TRY(ilu_apply_nv<2>(ctx, P, v)); break;
         case 3: MFB_TRY(ilu_apply_nv<3>(ctx, P, v)); break;
         default: MFB_TRY(ilu_apply_nv<4>(ctx, P, v)); break;
+    }
+    if (win) {
+        attr.accessPolicyWindow.num_bytes = 0;
+        MFB_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
     }
     MFB_CUDA(cudaGetLastError());
     return MFB_OK;

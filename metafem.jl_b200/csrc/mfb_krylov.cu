@@ -850,23 +850,40 @@ template <int LDK> __device__ __forceinline__ double ld_stream_f64(const double*
     asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
-template <int LDK> __device__ __forceinline__ double ld_stream_f64(const float* p) { return (double)__ldcs(p); }   // FP32-stored factors
+template <int LDK> __device__ __forceinline__ double ld_stream_val(const double* p) { return ld_stream_f64<LDK>(p); }
+template <int LDK> __device__ __forceinline__ float ld_stream_val(const float* p) { return __ldcs(p); }            // FP32-stored factors
 template <int LDK> __device__ __forceinline__ int ld_stream_s32(const int* p) {
     if constexpr (LDK == 0) return __ldg(p);
     int v;
     asm volatile("ld.global.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
-template <int LDK> __device__ __forceinline__ double ld_gather_f64(const double* p) {
-    if constexpr (LDK != 2) return __ldg(p);
-    double v;
-    asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
+// LDK = 3: the gathered vector is asked to stay in L2 (evict_last policy) while the factor / matrix streams pass through
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+template <int LDK> __device__ __forceinline__ double ld_gather_f64(const double* p, unsigned long long pol = 0) {
+    if constexpr (LDK == 3) {
+        double v;
+        asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+        return v;
+    } else if constexpr (LDK != 2) {
+        return __ldg(p);
+    } else {
+        double v;
+        asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
+        return v;
+    }
+}
+__device__ __forceinline__ void st_hint_f64(double* p, double v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
 }
 
 // the stream loop of one warp (its RW consecutive rows)
 // OUT = 0: y[row] = sum (the product). OUT = 1 / 2: one level of a triangular sweep on packed factors (mfb_ilu.cu): the "rows" are
-// positions in level order, rowid[] their node ids, x == y == v:  v[id] -= sum  /  v[id] = dinv[id] (v[id] - sum)
+// positions in level order, rowid[] their node ids, x == y == v:  v[id] -= sum  /  v[id] = dinv[id] v[id] - sum (rows pre-scaled)
 template <int NV, int UNR, int RW, int LDK, int OUT = 0, typename VT = double>
 __device__ __forceinline__ void spmv_mr_rows(const int* __restrict__ nodeptr, const int* __restrict__ nodecol, const VT* __restrict__ K,
                                           const double* x, double* y, int64_t N, int64_t row0,
@@ -877,22 +894,29 @@ __device__ __forceinline__ void spmv_mr_rows(const int* __restrict__ nodeptr, co
     const int lane = threadIdx.x & 31;
     const int le = lane / B, ik = lane - le * B, i = ik / NV, k = ik - i * NV;
     const bool on = lane < ACTIVE;
+    unsigned long long pol = 0;
+    if constexpr (LDK == 3) pol = l2_policy_evict_last();
     const double* xk = x + k;
     const int nr = (int)min((int64_t)RW, N - row0);
     const int myp = (lane <= nr) ? __ldg(nodeptr + row0 + lane) : 0;     // lane l holds nodeptr[row0 + l]
     // sweeps: the row's own entries of v (and its inverse diagonal block) are fetched now, while the stream runs -- a load at the
     // row end would stall the warp once per (short) row. Lane q < nr * NV holds component q % NV of row q / NV.
     int myid = 0;
-    double myv = 0.0, myd[OUT == 2 ? NV : 1];
+    double myv = 0.0;
     if constexpr (OUT != 0) {
         static_assert(OUT == 0 || RW * NV <= 32, "own entries of the warp's rows are held one per lane");
         myid = (lane < nr) ? __ldg(rowid + row0 + lane) : 0;
         const int idq = __shfl_sync(FULL, myid, (lane / NV) & 31);
         const bool has = lane < nr * NV;
         myv = has ? y[(size_t)idq * NV + lane % NV] : 0.0;
-        if constexpr (OUT == 2) {
+        if constexpr (OUT == 2) {                                        // the upper entries are pre-scaled: own value <- U_ii^-1 v_i, once per warp
+            double t = 0.0;
 #pragma unroll
-            for (int m = 0; m < NV; ++m) myd[m] = has ? __ldg(dinv + (size_t)idq * B + (lane % NV) * NV + m) : 0.0;
+            for (int m = 0; m < NV; ++m) {
+                const double d = has ? __ldg(dinv + (size_t)idq * B + (lane % NV) * NV + m) : 0.0;
+                t = fma(d, __shfl_sync(FULL, myv, ((lane / NV) * NV + m) & 31), t);
+            }
+            myv = t;
         }
     }
     const int s = __shfl_sync(FULL, myp, 0);
@@ -901,38 +925,39 @@ __device__ __forceinline__ void spmv_mr_rows(const int* __restrict__ nodeptr, co
     int cr = 0, lo = 0, hi = __shfl_sync(FULL, myp, 1) - s;              // current row and its entry range within the stream
     const VT* Kp = K + (size_t)s * B + lane;
     const int* Cp = nodecol + s + le;
-    double a[UNR], v[UNR];
+    double a[UNR];
+    VT v[UNR];                                                             // values stay in their storage type until they are used
     int c[UNR];
     int e = le, base = 0;
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
         a[u] = 0.0;
         const bool ok = e + u * EPW < deg;
-        v[u] = ok ? ld_stream_f64<LDK>(Kp + u * ACTIVE) : 0.0;
+        v[u] = ok ? ld_stream_val<LDK>(Kp + u * ACTIVE) : VT(0);
         c[u] = ok ? ld_stream_s32<LDK>(Cp + u * EPW) : 0;
     }
     for (;;) {
-        double vn[UNR];
+        VT vn[UNR];
         int cn[UNR];
         Kp += UNR * ACTIVE;
         Cp += UNR * EPW;
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {                                  // streams of the NEXT batch first ...
             const bool ok = e + W + u * EPW < deg;
-            vn[u] = ok ? ld_stream_f64<LDK>(Kp + u * ACTIVE) : 0.0;
+            vn[u] = ok ? ld_stream_val<LDK>(Kp + u * ACTIVE) : VT(0);
             cn[u] = ok ? ld_stream_s32<LDK>(Cp + u * EPW) : 0;
         }
         double xg[UNR];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) xg[u] = ld_gather_f64<LDK>(xk + (size_t)c[u] * NV);   // ... then the dependent gathers of this one
+        for (int u = 0; u < UNR; ++u) xg[u] = ld_gather_f64<LDK>(xk + (size_t)c[u] * NV, pol);   // ... then the dependent gathers of this one
         const int bend = base + W;
         if (bend < hi) {                                                  // the whole batch lies inside row cr
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) a[u] = fma(v[u], xg[u], a[u]);
+            for (int u = 0; u < UNR; ++u) a[u] = fma((double)v[u], xg[u], a[u]);
         } else {                                                          // the batch reaches the end of row cr
             double p[UNR];
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) p[u] = v[u] * xg[u];
+            for (int u = 0; u < UNR; ++u) p[u] = (double)v[u] * xg[u];
             for (;;) {
 #pragma unroll
                 for (int u = 0; u < UNR; ++u) {
@@ -957,16 +982,10 @@ __device__ __forceinline__ void spmv_mr_rows(const int* __restrict__ nodeptr, co
                     if (le == 0 && k == 0 && on) y[(size_t)(row0 + cr) * NV + i] = r;
                 } else {
                     const int id = __shfl_sync(FULL, myid, cr);
-                    const bool wr = le == 0 && k == 0 && on;
-                    const int src = (cr * NV + i) & 31;
-                    const double yi = __shfl_sync(FULL, myv, src) - r;
-                    if constexpr (OUT == 1) {
-                        if (wr) y[(size_t)id * NV + i] = yi;
-                    } else {
-                        double z = 0.0;
-#pragma unroll
-                        for (int m = 0; m < NV; ++m) z = fma(__shfl_sync(FULL, myd[m], src), __shfl_sync(FULL, yi, m * NV), z);
-                        if (wr) y[(size_t)id * NV + i] = z;
+                    const double yi = __shfl_sync(FULL, myv, (cr * NV + i) & 31) - r;
+                    if (le == 0 && k == 0 && on) {
+                        if constexpr (LDK == 3) st_hint_f64(y + (size_t)id * NV + i, yi, pol);
+                        else y[(size_t)id * NV + i] = yi;
                     }
                 }
                 ++cr;
@@ -1385,24 +1404,24 @@ void launch_spmv_mr(mfb_ctx* ctx, const double* K, const double* x, double* y, c
     else k_spmv_mr<NV, SpmvUnroll<NV>::value, RW, false, MINB><<<grid, 256, 0, ctx->stream>>>(ctx->nodeptr.p, ctx->nodecol.p, K, x, y, N, w, R.sc, R.red, R.partials, R.counter, op.op);
     ctx->launches++;
 }
-template <int NV, int UNR, int RW, int OUT, int MINB, typename VT>
+template <int NV, int UNR, int RW, int OUT, int MINB, typename VT, int LDK>
 __global__ void __launch_bounds__(256, MINB) k_sweep_mr(const int* __restrict__ ptr, const int* __restrict__ col, const VT* __restrict__ val,
                                                         double* v, int w0, int w1, const int* __restrict__ rowid, const double* __restrict__ dinv) {
     const int64_t row0 = w0 + (blockIdx.x * (int64_t)8 + (threadIdx.x >> 5)) * RW;
-    if (row0 < w1) spmv_mr_rows<NV, UNR, RW, 0, OUT, VT>(ptr, col, val, v, v, (int64_t)w1, row0, rowid, dinv);
+    if (row0 < w1) spmv_mr_rows<NV, UNR, RW, LDK, OUT, VT>(ptr, col, val, v, v, (int64_t)w1, row0, rowid, dinv);
 }
-template <int NV, int RW, int UNR, int MINB>
+template <int NV, int RW, int UNR, int MINB, int LDK = 0>
 void launch_sweep_mr(mfb_ctx* ctx, bool upper, const int* ptr, const int* col, const void* val, bool f32, const int* rowid, const double* dinv,
                      double* v, int w0, int w1) {
     const unsigned grid = (unsigned)((w1 - w0 + 8 * RW - 1) / (8 * RW));
     const float* vf = static_cast<const float*>(val);
     const double* vd = static_cast<const double*>(val);
     if (f32) {
-        if (upper) k_sweep_mr<NV, UNR, RW, 2, MINB, float><<<grid, 256, 0, ctx->stream>>>(ptr, col, vf, v, w0, w1, rowid, dinv);
-        else k_sweep_mr<NV, UNR, RW, 1, MINB, float><<<grid, 256, 0, ctx->stream>>>(ptr, col, vf, v, w0, w1, rowid, dinv);
+        if (upper) k_sweep_mr<NV, UNR, RW, 2, MINB, float, LDK><<<grid, 256, 0, ctx->stream>>>(ptr, col, vf, v, w0, w1, rowid, dinv);
+        else k_sweep_mr<NV, UNR, RW, 1, MINB, float, LDK><<<grid, 256, 0, ctx->stream>>>(ptr, col, vf, v, w0, w1, rowid, dinv);
     } else {
-        if (upper) k_sweep_mr<NV, UNR, RW, 2, MINB, double><<<grid, 256, 0, ctx->stream>>>(ptr, col, vd, v, w0, w1, rowid, dinv);
-        else k_sweep_mr<NV, UNR, RW, 1, MINB, double><<<grid, 256, 0, ctx->stream>>>(ptr, col, vd, v, w0, w1, rowid, dinv);
+        if (upper) k_sweep_mr<NV, UNR, RW, 2, MINB, double, LDK><<<grid, 256, 0, ctx->stream>>>(ptr, col, vd, v, w0, w1, rowid, dinv);
+        else k_sweep_mr<NV, UNR, RW, 1, MINB, double, LDK><<<grid, 256, 0, ctx->stream>>>(ptr, col, vd, v, w0, w1, rowid, dinv);
     }
     ctx->launches++;
 }
@@ -1413,18 +1432,20 @@ void launch_sweep_mr(mfb_ctx* ctx, bool upper, const int* ptr, const int* col, c
 // false: n_var without this kernel.
 bool mfb_sweep_level_mr(mfb_ctx* ctx, bool upper, const int* ptr, const int* col, const void* val, bool f32, const int* rowid,
                         const double* dinv, double* v, int w0, int w1) {
-    static const int cfg = [] { const char* e = getenv("MFB_ILU_CFG"); return e ? atoi(e) : 0; }();   // tuning aid
+    static const int cfg = [] { const char* e = getenv("MFB_ILU_CFG"); return e ? atoi(e) : 0; }();   // tuning aid (profiles/ilu_r2.md)
     switch (ctx->n_var) {
-        case 1: launch_sweep_mr<1, 8, 2, 4>(ctx, upper, ptr, col, val, f32, rowid, dinv, v, w0, w1); return true;
-        case 2: launch_sweep_mr<2, 8, 3, 4>(ctx, upper, ptr, col, val, f32, rowid, dinv, v, w0, w1); return true;
+        case 1: launch_sweep_mr<1, 8, 2, 4, 3>(ctx, upper, ptr, col, val, f32, rowid, dinv, v, w0, w1); return true;
+        case 2: launch_sweep_mr<2, 8, 3, 4, 3>(ctx, upper, ptr, col, val, f32, rowid, dinv, v, w0, w1); return true;
         case 3:
             switch (cfg) {
-                case 1: launch_sweep_mr<3, 8, 4, 4>(ctx, upper, ptr, col, val, f32, rowid, dinv, v, w0, w1); break;
-                case 2: launch_sweep_mr<3, 4, 4, 4>(ctx, upper, ptr, col, val, f32, rowid, dinv, v, w0, w1); break;
-                default: launch_sweep_mr<3, 8, 5, 3>(ctx, upper, ptr, col, val, f32, rowid, dinv, v, w0, w1); break;   // best of the variants measured (profiles/ilu_r2.md)
+                case 1: launch_sweep_mr<3, 8, 4, 4, 3>(ctx, upper, ptr, col, val, f32, rowid, dinv, v, w0, w1); break;
+                case 2: launch_sweep_mr<3, 8, 5, 4, 0>(ctx, upper, ptr, col, val, f32, rowid, dinv, v, w0, w1); break;   // without the L2 hint
+                case 3: launch_sweep_mr<3, 8, 5, 3, 3>(ctx, upper, ptr, col, val, f32, rowid, dinv, v, w0, w1); break;
+                case 4: launch_sweep_mr<3, 4, 5, 4, 3>(ctx, upper, ptr, col, val, f32, rowid, dinv, v, w0, w1); break;
+                default: launch_sweep_mr<3, 8, 5, 4, 3>(ctx, upper, ptr, col, val, f32, rowid, dinv, v, w0, w1); break;
             }
             return true;
-        case 4: launch_sweep_mr<4, 8, 5, 3>(ctx, upper, ptr, col, val, f32, rowid, dinv, v, w0, w1); return true;
+        case 4: launch_sweep_mr<4, 8, 5, 3, 3>(ctx, upper, ptr, col, val, f32, rowid, dinv, v, w0, w1); return true;
         default: return false;
     }
 }
