@@ -664,6 +664,8 @@ def main():
         try:
             ilu = case.ilu_solve()
             ilu["jacobi_only"] = {"solve_ms": r["solve_ms"], "krylov_iterations": r["krylov_iterations"]["mean"]}
+            ilu["newton_step_ms_with_pl_ilu"] = r["ms_per_step"] - r["solve_ms"] + ilu["solve_ms"]   # same assembly, the other solve
+            ilu["newton_step_dof_per_s_with_pl_ilu"] = case.ndof_global / (ilu["newton_step_ms_with_pl_ilu"] * 1e-3)
         except Exception as e:
             ilu = {"failed": f"{type(e).__name__}: {e}"}
     peak, peak_kind = hbm_peak()

@@ -56,8 +56,9 @@ enum { MFB_PR_JACOBI = 0 /* Pr_Jacobi! by diagonal (default) */, MFB_PR_JACOBI_C
        MFB_PR_IDENTITY = 2 };
 enum { MFB_PL_IDENTITY = 0 /* default */, MFB_PL_JACOBI = 1 /* Pl_Jacobi by diagonal */, MFB_PL_JACOBI_ROW = 2 /* normalized_by_row */,
        MFB_PL_ILU = 3 /* Pl_ILU (:179-194): zero-fill block ILU of the right-scaled matrix, level-scheduled sweeps; elimination order
-                         chosen for parallelism (hash ranking) where cuSPARSE ilu02! follows the row order -- same incomplete
-                         factorisation property, solutions agree at solver tolerance */ };
+                         chosen for parallelism (colour classes of a greedy colouring) where cuSPARSE ilu02! follows the row order,
+                         packed factors of the sweeps stored in FP32 (MFB_ILU_FP64=1: doubles) -- same incomplete factorisation
+                         property, solutions agree at solver tolerance */ };
 
 /* vectors of GlobalField (src/solver/01_Types.jl:110-132) */
 enum { MFB_VEC_X = 0, MFB_VEC_DX = 1, MFB_VEC_X_STAR = 2, MFB_VEC_RESIDUE = 3 };

@@ -4,16 +4,23 @@
 // (src/solver/linear_solver/02_Preconditioner.jl:179-194), on the right-Jacobi-scaled matrix (:38-40). cuSPARSE factorises in
 // the matrix's own row order and finds its parallelism by level analysis; on a 3-D FEM graph in a locality-preserving order
 // that gives O(10^3) dependency levels, i.e. thousands of tiny launches per application. Here the SAME incomplete
-// factorisation -- zero fill, (L U)_ij = A_ij on the pattern -- is taken in an elimination order chosen for the machine: nodes
-// are ranked by a hash of their index, the dependency levels of that order number a few dozen (the longest increasing path of a
-// random ranking on a bounded-degree graph), and each level is one launch with one warp per block row. The blocks are the
-// n_var x n_var node blocks of the library's matrix format: block ILU(0) without pivoting, unit lower factor
+// factorisation -- zero fill, (L U)_ij = A_ij on the pattern -- is taken in an elimination order chosen for the machine: the
+// nodes are coloured greedily in the priority order of a hash of their global id, and eliminated colour class by colour class
+// (ties by the hash). The dependency levels are then bounded by the number of colours (32 at 88^3 hex20; a plain hash order has
+// 127, MFB_ILU_ORDER=hash), each level is one launch, and the iteration counts were lower than with the plain hash order. The
+// blocks are the n_var x n_var node blocks of the library's matrix format: block ILU(0) without pivoting, unit lower factor
 // (L_ik = A_ik U_kk^-1), the inverted diagonal blocks kept aside.
-//   setup  (per pattern)  elimination rank, lower/upper flags per entry, levels, rows by level, lower entries in elimination order
+//   setup  (per pattern)  colouring, elimination rank, lower/upper flags per entry, levels, rows by level, lower entries in
+//                         elimination order, index arrays of the packed factors
 //   factor (per solve)    level by level, one warp per row: for every lower entry k in order, L_ik and the update of row i by the
-//                         upper part of row k (positions found by binary search in row i); then the inverse of U_ii
-//   apply  (per product)  forward sweep over the levels (unit L), backward sweep (U with the stored inverses), in place
+//                         upper part of row k (positions found by binary search in row i); then the inverse of U_ii. Then the
+//                         factors are PACKED for the sweeps: per direction, rows in level order with their entries contiguous,
+//                         values rounded to FP32 (see ilu_use_f32), upper rows pre-multiplied by U_ii^-1
+//   apply  (per product)  forward sweep over the levels (unit L), backward sweep, in place, each level on the multi-row stream
+//                         loop of the SpMV (mfb_sweep_level_mr in mfb_krylov.cu); one-warp-per-row kernels remain for n_var > 4
+//                         and as A/B switches (MFB_ILU_SWEEP=row, MFB_ILU_UNPACKED=1)
 // Everything a row receives is written by its own warp: the factorisation and the sweeps are bit-reproducible.
+// Measurements and what bounds the sweeps: profiles/ilu_r2.md.
 #include <cstdio>
 #include <cstring>
 #include <thrust/device_ptr.h>
@@ -632,41 +639,11 @@ int mfb_ilu_apply(mfb_ctx* ctx, double* v) {
     MFB_REQUIRE(it != ilu_table().end() && it->second->factored, MFB_ERR_STATE, "Pl_ILU applied before it was factorised");
     IluPlan* P = it->second;
     ProfScope ps(ctx, MFB_T_PRECOND);
-    // experiment (MFB_ILU_L2WIN=1): the swept vector as a persisting access-policy window of the stream
-    static const bool win = [] { const char* e = getenv("MFB_ILU_L2WIN"); return e && e[0] == '1'; }();
-    cudaStreamAttrValue attr;
-    memset(&attr, 0, sizeof(attr));
-    if (win) {
-        static size_t max_win = 0;
-        if (!max_win) {
-            cudaDeviceProp prop;
-            MFB_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
-            size_t aside = (size_t)prop.persistingL2CacheMaxSize;
-            const size_t want = (size_t)ctx->N * ctx->n_var * sizeof(double) * 5 / 4;
-            if (aside > want) aside = want;
-            MFB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, aside));
-            max_win = (size_t)prop.accessPolicyMaxWindowSize;
-            fprintf(stderr, "[mfb ilu] persisting L2 set-aside %zu MB (max %d MB), window max %zu MB\n", aside >> 20,
-                    prop.persistingL2CacheMaxSize >> 20, max_win >> 20);
-        }
-        size_t bytes = (size_t)ctx->N * ctx->n_var * sizeof(double);
-        if (bytes > max_win) bytes = max_win;
-        attr.accessPolicyWindow.base_ptr = v;
-        attr.accessPolicyWindow.num_bytes = bytes;
-        attr.accessPolicyWindow.hitRatio = 1.0f;
-        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        MFB_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
-    }
     switch (ctx->n_var) {
         case 1: MFB_TRY(ilu_apply_nv<1>(ctx, P, v)); break;
         case 2: MFB_TRY(ilu_apply_nv<2>(ctx, P, v)); break;
         case 3: MFB_TRY(ilu_apply_nv<3>(ctx, P, v)); break;
         default: MFB_TRY(ilu_apply_nv<4>(ctx, P, v)); break;
-    }
-    if (win) {
-        attr.accessPolicyWindow.num_bytes = 0;
-        MFB_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
     }
     MFB_CUDA(cudaGetLastError());
     return MFB_OK;
