@@ -61,6 +61,9 @@ WORKLOADS = {
     # name: (BASELINE config, box side, solver of the script, converge_tol, label)
     "neo_hookean": dict(cfg=2, box=88, solver=SOLVER, tol=TOL,
                         label="examples/hyper_elasticity: Neo-Hookean Newton step, hex20 x 27 Gauss points"),
+    "thermal_conduction": dict(cfg=0, box=100, solver=dict(Sv_func="idrs", maxiter=2000, max_pass=20, s=8), tol=1e-6,
+                               label="examples/thermal_conduction: steady heat conduction with convection boundaries (1 field; the script's "
+                                     "weak form and solver on a synthetic box instead of the bundled tet mesh), hex20"),
     "linear_elasticity": dict(cfg=1, box=43, solver=dict(Sv_func="idrs", maxiter=2000, max_pass=20, s=8), tol=1e-5,
                               label="examples/linear_elasticity: 3-D linear elasticity Newton step (cantilever script's solver), hex20"),
     "thermo_elasticity": dict(cfg=3, box=62, solver=dict(Sv_func="bicgstabl_GS", maxiter=2000, max_pass=20, s=8), tol=1e-6,
@@ -283,6 +286,7 @@ class Env:
 def make_spec(name):
     from metafem_jl_b200.frontend import weakform as wf
     return {"neo_hookean": lambda: wf.neo_hookean(fixed_bg=1, traction_bg=2),
+            "thermal_conduction": lambda: wf.thermal_conduction(bgs=(1, 2)),          # 3D_Script.jl:21-35, convection on both ends
             # E = 1e6, nu = 0.3 (lambda, mu = 0.5769e6, 0.3846e6), penalty 1000 E as in the cantilever script (3D_Script.jl:45-63)
             "linear_elasticity": lambda: wf.linear_elasticity(0.5769e6, 0.3846e6, 1e9, fixed_bg=1, traction_bgs=((2, "sl"),)),
             "thermo_elasticity": lambda: wf.thermo_elasticity(fixed_bg=1, thermal_bg=2),
@@ -324,10 +328,14 @@ class Case:
             cid = env.comm_id()
             with env.torch.cuda.stream(env.stream):
                 m.init_distributed(fd, self.sub, env.rank, env.world, cid)
-        for b, v in zip(("d1", "d2", "d3"), gstate):
-            fd.controlpoints[b][:] = pick(v)
+        if name != "thermal_conduction":
+            for b, v in zip(("d1", "d2", "d3"), gstate):
+                fd.controlpoints[b][:] = pick(v)
         lx = tables.x
-        if name == "neo_hookean":
+        if name == "thermal_conduction":
+            fd.controlpoints["T"][:] = 293.15 + 20.0 * np.cos(3.0 * lx[1]) * lx[0]
+            fd.controlpoints["s"][:] = 1000.0
+        elif name == "neo_hookean":
             fd.controlpoints["Pl1"][:] = LOAD
             fd.global_vars.update(mu=MU, lam=LAM, tau_b=1000 * max(MU, LAM))
         elif name == "thermo_elasticity":
@@ -738,7 +746,7 @@ def main():
     # ---- the other BASELINE configs (N = 1), the partitioned J2 step (N > 1) ---------------------------------------------
     extras = {}
     if not args.no_extras and not args.ncu and name == "neo_hookean":
-        todo = (["linear_elasticity", "thermo_elasticity", "j2_fused", "j2"] if world == 1 else ["j2_fused"])
+        todo = (["thermal_conduction", "linear_elasticity", "thermo_elasticity", "j2_fused", "j2"] if world == 1 else ["j2_fused"])
         for wn in todo:
             try:
                 c2 = Case(env, wn, WORKLOADS[wn]["box"], args.numbering)
