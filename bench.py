@@ -642,7 +642,7 @@ def main():
             case.step(False, True)
         torch.cuda.synchronize()
         out = [case.ilu_solve() for _ in range(2)]
-        print(json.dumps({"ilu_only": out, "order": os.environ.get("MFB_ILU_ORDER", "color"), "sweep": os.environ.get("MFB_ILU_SWEEP", "stream"), "rw": os.environ.get("MFB_ILU_RW", "8"), "workload": name, "box": n}))
+        print(json.dumps({"ilu_only": out, "order": os.environ.get("MFB_ILU_ORDER", "color"), "sweep": os.environ.get("MFB_ILU_SWEEP", "stream"), "cfg": os.environ.get("MFB_ILU_CFG", "0"), "workload": name, "box": n}))
         return
     if args.assembly_only:
         r = measure(case, K, W, e2e=False, solve=False)
