@@ -1277,7 +1277,6 @@ __global__ void k_sc_gamma(double* sc, int S) {                                 
         sc[SC_GAMPP + j] = gam[j + 1] + d;
     }
 }
-__global__ void k_sc_store(double* sc, int at, const double* red) { sc[at] = red[0]; }
 
 // ---- device-resident scalars of idrs! (04_IDRs.jl:26-95). Layout: [0] omega [1] beta [2] alpha [8 + i] f [8 + S + i] c
 // [8 + 2S + i] -omega*c [8 + 3S + i*S + k] M[i][k]
@@ -1722,7 +1721,6 @@ struct FB {
 // r = Pl(b - A x) (the opening lines of every solver) or, with left == false, the plain b - A x of iterative_Solve!;
 // returns the normalized norm
 int true_residual(Solver& S, double* r, const double* b, const double* x, double* res, bool left = true) {
-    mfb_ctx* ctx = S.ctx;
     const double* keep = S.pl;
     const bool keep_ilu = S.pl_ilu;
     S.pl = nullptr; S.pl_ilu = false;
@@ -1741,7 +1739,6 @@ int true_residual(Solver& S, double* r, const double* b, const double* x, double
     } else {
         MFB_TRY(S.lincomb(r, -1.0, 1, c, xs, &n2));
     }
-    (void)ctx;
     *res = S.nn(n2);
     return MFB_OK;
 }

@@ -30,11 +30,6 @@ namespace {
 constexpr int TPB = 256;
 inline unsigned nblk(int64_t n) { return (unsigned)((n + TPB - 1) / TPB); }
 
-__global__ void k_first_touch(const int* conn_ref, int64_t n, unsigned long long* key) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) atomicMin(key + conn_ref[i], (unsigned long long)i);
-}
-
 __device__ __forceinline__ unsigned long long spread21(unsigned long long v) {   // 21 bits -> every third bit
     v &= 0x1fffffull;
     v = (v | v << 32) & 0x1f00000000ffffull;
@@ -95,15 +90,6 @@ __global__ void k_pair_keys(const int* conn, int n_a, int64_t n_el, unsigned lon
     unsigned long long a = (unsigned)conn[e * n_a + p / n_a], b = (unsigned)conn[e * n_a + p % n_a];
     keys[i] = (a << 32) | b;
 }
-
-__global__ void k_split(const unsigned long long* keys, int64_t U, int* col) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < U) col[i] = (int)(keys[i] & 0xffffffffull);
-}
-
-struct RowKey {
-    __host__ __device__ unsigned long long operator()(int64_t r) const { return ((unsigned long long)r) << 32; }
-};
 
 // entry of node pair p of the element item_elem[item] (binary search in the element's first node's row)
 __global__ void k_emap_items(const int* conn, const int* nodeptr, const int* nodecol, int n_a, const int* item_elem, int64_t n_items, int* out) {

@@ -130,10 +130,6 @@ __global__ void k_boundary_hosts(const int* bface /*[nfb][nb]*/, const int* cnt,
     const int f = bface[t] - 1;
     if (cnt[f] == 1) { b_el[brank[f]] = (int)b + 1; b_eidx[brank[f]] = pos + 1; }
 }
-__global__ void k_transpose_in(const int* src /*[vpb][nb] col-major == [nb][vpb]*/, int64_t nb, int vpb, int* dst) {
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t < nb * vpb) dst[t] = src[t];
-}
 
 // ---- FEM_Dict, sequential insertion (06_GPU_Dict.jl) ------------------------------------------------------------------------
 __device__ __forceinline__ u64 wang64(u64 a) {                       // GPU_hash_64_64 (:2-11)
