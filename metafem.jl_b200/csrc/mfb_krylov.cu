@@ -834,6 +834,68 @@ __global__ void __launch_bounds__(256) k_fused(const Fused* __restrict__ Fg, con
     }
 }
 
+// Programs without updates (the dots that follow a product: r_shadow' A u, and the opening row of the MR part). In k_fused such a
+// program has one or two 16-byte loads per thread in flight -- 57 us for a 134 MB dot, 2.3 TB/s (profiles/launches_r2g). Here
+// every thread takes J pairs per step and issues all 2 J ND loads before the first multiply.
+template <int ND, int J>
+__global__ void __launch_bounds__(256, 3) k_dots(const Fused* __restrict__ Fg, const RedCtx R, int64_t n, const unsigned char* owned,
+                                                 int nv) {
+    if (stopped(R)) return;
+    __shared__ const double* s_x[ND];
+    __shared__ const double* s_y[ND];
+    __shared__ ScOp s_ops[2];
+    __shared__ int s_nd;
+    __shared__ double s_w[8];
+    const int tid = threadIdx.x;
+    if (tid < ND) { s_x[tid] = Fg->dx[tid]; s_y[tid] = Fg->dy[tid]; }
+    if (tid == 32) { s_ops[0] = Fg->ops[0]; s_ops[1] = Fg->ops[1]; s_nd = Fg->n_dot; }
+    __syncthreads();
+    const int nd = s_nd;
+    const double* xp[ND];
+    const double* yp[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { xp[d] = d < nd ? s_x[d] : nullptr; yp[d] = d < nd ? s_y[d] : nullptr; }
+    double acc[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) acc[d] = 0.0;
+    const int64_t np = (n + 1) >> 1;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    const double2 zero2 = make_double2(0.0, 0.0);
+    for (int64_t p0 = blockIdx.x * (int64_t)256 + tid; p0 < np; p0 += J * stride) {
+        double2 xv[J][ND], yv[J][ND];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int64_t pj = p0 + j * stride;
+            const bool in = pj < np;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                xv[j][d] = (in && xp[d]) ? ld2(xp[d], pj, n) : zero2;
+                yv[j][d] = (in && yp[d]) ? (yp[d] == xp[d] ? xv[j][d] : ld2(yp[d], pj, n)) : zero2;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int64_t pj = p0 + j * stride;
+            if (pj < np) {
+                double2 w0 = make_double2(1.0, 2 * pj + 1 < n ? 1.0 : 0.0);
+                if (owned != nullptr) {                     // count every node once (on its owner)
+                    w0.x = owned[(2 * pj) / nv] ? 1.0 : 0.0;
+                    if (w0.y != 0.0) w0.y = owned[(2 * pj + 1) / nv] ? 1.0 : 0.0;
+                }
+#pragma unroll
+                for (int d = 0; d < ND; ++d) acc[d] += w0.x * (xv[j][d].x * yv[j][d].x) + w0.y * (xv[j][d].y * yv[j][d].y);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+        if (d < nd) {
+            const double w = block_sum256(acc[d], s_w);
+            if (tid == 0) R.partials[(size_t)d * gridDim.x + blockIdx.x] = w;
+        }
+    reduce_tail(R, nd, s_ops[0], s_ops[1]);
+}
+
 // ---- SpMV, multi-row streams: one warp walks the CONCATENATED value stream of RW consecutive block rows (they are contiguous
 // in memory) with the same software pipeline as k_spmv_bsr, so the dependent chain nodeptr -> (values, column ids) -> x[col]
 // is restarted once per RW rows (~ 8 x 4 batches) instead of once per row (~ 4 batches: about one exposed DRAM latency in
@@ -1665,6 +1727,11 @@ struct Solver {
         }
         ProfScope ps(ctx, MFB_T_REDUCE);
         const RedCtx R = redctx();
+        if (F.n_upd == 0 && nd <= 2) {                     // one or two plain dots: more loads in flight per thread
+            if (nd == 1) LAUNCH((k_dots<1, 4>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
+            else LAUNCH((k_dots<2, 2>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
+            return after_reduce(R, nd, F.ops[0], F.ops[1]);
+        }
         if (nd <= 2) LAUNCH((k_fused<2>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
         else if (nd <= 4) LAUNCH((k_fused<4>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
         else if (nd <= 8) LAUNCH((k_fused<8>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
