@@ -896,6 +896,107 @@ __global__ void __launch_bounds__(256, 3) k_dots(const Fused* __restrict__ Fg, c
     reduce_tail(R, nd, s_ops[0], s_ops[1]);
 }
 
+// Light programs: at most two single-term updates y_u = ay y_u + c x_u followed by at most four dots (the first BiCG updates,
+// every row of the MR part). k_fused has 2-5 loads per thread in flight for them; here a thread takes J pairs per step and
+// issues all their loads first (NU updates, ND dots and J are template parameters so that the register arrays fit). The host checks (light_ok) that no load can observe a store of the same program: the update
+// targets are distinct and are read neither by a later update nor -- through a pointer -- by a dot.
+template <int NU, int ND, int J>
+__global__ void __launch_bounds__(256, 3) k_light(const Fused* __restrict__ Fg, const RedCtx R, int64_t n, const unsigned char* owned,
+                                                  int nv) {
+    if (stopped(R)) return;
+    __shared__ double* s_y[NU];
+    __shared__ const double* s_x[NU];
+    __shared__ double s_ay[NU], s_c[NU];
+    __shared__ const double* s_dx[ND > 0 ? ND : 1];
+    __shared__ const double* s_dy[ND > 0 ? ND : 1];
+    __shared__ ScOp s_ops[2];
+    __shared__ int s_cnt[2];
+    __shared__ double s_w[8];
+    const int tid = threadIdx.x;
+    if (tid < NU && tid < Fg->n_upd) {
+        const FusedUpd u = Fg->u[tid];
+        const FusedTerm t = Fg->t[u.t0];
+        s_y[tid] = u.y;
+        s_x[tid] = t.x;
+        s_ay[tid] = u.ayp ? u.ay * __ldcg(u.ayp) : u.ay;
+        s_c[tid] = t.cp ? t.c * __ldcg(t.cp) : t.c;
+    }
+    if (tid >= 32 && tid < 32 + ND && tid - 32 < Fg->n_dot) { s_dx[tid - 32] = Fg->dx[tid - 32]; s_dy[tid - 32] = Fg->dy[tid - 32]; }
+    if (tid == 64) { s_ops[0] = Fg->ops[0]; s_ops[1] = Fg->ops[1]; s_cnt[0] = Fg->n_upd; s_cnt[1] = Fg->n_dot; }
+    __syncthreads();
+    const int nu = s_cnt[0], nd = s_cnt[1];
+    double* yp[NU];
+    const double* xp[NU];
+    double ay[NU], c[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+        const bool live = u < nu;
+        yp[u] = live ? s_y[u] : nullptr; xp[u] = live ? s_x[u] : nullptr;
+        ay[u] = live ? s_ay[u] : 0.0; c[u] = live ? s_c[u] : 0.0;
+    }
+    const double* dxp[ND > 0 ? ND : 1];
+    const double* dyp[ND > 0 ? ND : 1];
+    double acc[ND > 0 ? ND : 1];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { dxp[d] = d < nd ? s_dx[d] : nullptr; dyp[d] = d < nd ? s_dy[d] : nullptr; acc[d] = 0.0; }
+    const int64_t np = (n + 1) >> 1;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    const double2 zero2 = make_double2(0.0, 0.0);
+    for (int64_t p0 = blockIdx.x * (int64_t)256 + tid; p0 < np; p0 += J * stride) {
+        double2 yv[J][NU], xv[J][NU], dxv[J][ND > 0 ? ND : 1], dyv[J][ND > 0 ? ND : 1];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int64_t pj = p0 + j * stride;
+            const bool in = pj < np;
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                yv[j][u] = (in && yp[u] && ay[u] != 0.0) ? ld2(yp[u], pj, n) : zero2;
+                xv[j][u] = (in && xp[u]) ? ld2(xp[u], pj, n) : zero2;
+            }
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                dxv[j][d] = (in && dxp[d]) ? ld2(dxp[d], pj, n) : zero2;
+                dyv[j][d] = (in && dyp[d] && dyp[d] != dxp[d]) ? ld2(dyp[d], pj, n) : zero2;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int64_t pj = p0 + j * stride;
+            if (pj >= np) continue;
+            double2 r0 = zero2;                               // result of the last update (dot operand)
+#pragma unroll
+            for (int u = 0; u < NU; ++u)
+                if (u < nu) {
+                    r0 = make_double2(ay[u] * yv[j][u].x + c[u] * xv[j][u].x, ay[u] * yv[j][u].y + c[u] * xv[j][u].y);
+                    st2(yp[u], pj, n, r0);
+                }
+            if constexpr (ND > 0) {
+                double2 w0 = make_double2(1.0, 2 * pj + 1 < n ? 1.0 : 0.0);
+                if (owned != nullptr) {                       // count every node once (on its owner)
+                    w0.x = owned[(2 * pj) / nv] ? 1.0 : 0.0;
+                    if (w0.y != 0.0) w0.y = owned[(2 * pj + 1) / nv] ? 1.0 : 0.0;
+                }
+#pragma unroll
+                for (int d = 0; d < ND; ++d)
+                    if (d < nd) {
+                        const double2 X = dxp[d] ? dxv[j][d] : r0;
+                        const double2 Y = dyp[d] ? (dyp[d] == dxp[d] ? X : dyv[j][d]) : r0;
+                        acc[d] += w0.x * (X.x * Y.x) + w0.y * (X.y * Y.y);
+                    }
+            }
+        }
+    }
+    if constexpr (ND > 0) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+            if (d < nd) {
+                const double w = block_sum256(acc[d], s_w);
+                if (tid == 0) R.partials[(size_t)d * gridDim.x + blockIdx.x] = w;
+            }
+        reduce_tail(R, nd, s_ops[0], s_ops[1]);
+    }
+}
+
 // ---- SpMV, multi-row streams: one warp walks the CONCATENATED value stream of RW consecutive block rows (they are contiguous
 // in memory) with the same software pipeline as k_spmv_bsr, so the dependent chain nodeptr -> (values, column ids) -> x[col]
 // is restarted once per RW rows (~ 8 x 4 batches) instead of once per row (~ 4 batches: about one exposed DRAM latency in
@@ -1717,16 +1818,46 @@ struct Solver {
         MFB_CUDA(cudaStreamSynchronize(ctx->stream));     // progs may be rebuilt by the next pass
         return MFB_OK;
     }
+    // k_light's conditions: 1-2 single-term updates, <= 4 dots, and no load of the program can see one of its stores
+    static bool light_ok(const Fused& F) {
+        static const bool off = [] { const char* e = getenv("MFB_NO_LIGHT"); return e && e[0] == '1'; }();
+        if (off || F.n_upd < 1 || F.n_upd > 2 || F.n_dot > 4) return false;
+        for (int u = 0; u < F.n_upd; ++u) {
+            if (F.u[u].nt != 1) return false;
+            for (int v = 0; v < F.n_upd; ++v) {
+                if (v != u && F.u[v].y == F.u[u].y) return false;
+                if (F.t[F.u[v].t0].x == F.u[u].y) return false;          // also x == own y: (ay + c) y is legal but not worth a case
+            }
+            for (int d = 0; d < F.n_dot; ++d)
+                if (F.dx[d] == F.u[u].y || F.dy[d] == F.u[u].y) return false;
+        }
+        return true;
+    }
     int run(int idx) {
         const Fused& F = progs[idx];
         const Fused* dev = reinterpret_cast<const Fused*>(ctx->kprog.p) + idx;
         const int nd = F.n_dot;
+        const bool light = light_ok(F);
         if (nd == 0) {
-            LAUNCH((k_fused<0>), RED_BLOCKS, TPB, dev, stopctx(), n, (const unsigned char*)nullptr, ctx->n_var);
+            const RedCtx R0 = stopctx();
+            if (light && F.n_upd == 1) LAUNCH((k_light<1, 0, 4>), RED_BLOCKS, TPB, dev, R0, n, (const unsigned char*)nullptr, ctx->n_var);
+            else if (light) LAUNCH((k_light<2, 0, 2>), RED_BLOCKS, TPB, dev, R0, n, (const unsigned char*)nullptr, ctx->n_var);
+            else LAUNCH((k_fused<0>), RED_BLOCKS, TPB, dev, R0, n, (const unsigned char*)nullptr, ctx->n_var);
             return MFB_OK;
         }
         ProfScope ps(ctx, MFB_T_REDUCE);
         const RedCtx R = redctx();
+        if (light) {
+            if (F.n_upd == 1) {
+                if (nd == 1) LAUNCH((k_light<1, 1, 2>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
+                else if (nd == 2) LAUNCH((k_light<1, 2, 2>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
+                else LAUNCH((k_light<1, 4, 1>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
+            } else {
+                if (nd <= 2) LAUNCH((k_light<2, 2, 1>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
+                else LAUNCH((k_light<2, 4, 1>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
+            }
+            return after_reduce(R, nd, F.ops[0], F.ops[1]);
+        }
         if (F.n_upd == 0 && nd <= 2) {                     // one or two plain dots: more loads in flight per thread
             if (nd == 1) LAUNCH((k_dots<1, 4>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
             else LAUNCH((k_dots<2, 2>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
