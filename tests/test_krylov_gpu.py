@@ -10,10 +10,9 @@ from oracle import assembly as oasm, solver as osv
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["thermal", "linear_elasticity"])
-def system(request, built_lib):
+def _make_system(name):
     import metafem_b200 as m
-    dom, spec, mesh = build_case(request.param, (3, 2, 2))
+    dom, spec, mesh = build_case(name, (3, 2, 2))
     oasm.assemble_Global_Variables(dom)
     fd = product_from_oracle(dom)
     m.assemble_Global_Variables(fd)
@@ -32,7 +31,13 @@ def system(request, built_lib):
     fd.K_nonlinear_func(td, fem_domain=fd)
     gf = dom.globalfield
     A = oasm.csr_from_globalfield(gf)
-    yield dom, fd, A, spl.spsolve(A.tocsc(), gf.residue)
+    return dom, fd, A, spl.spsolve(A.tocsc(), gf.residue)
+
+
+@pytest.fixture(scope="module", params=["thermal", "linear_elasticity"])
+def system(request, built_lib):
+    dom, fd, A, exact = _make_system(request.param)
+    yield dom, fd, A, exact
     fd.close()
 
 
@@ -107,3 +112,25 @@ def test_pl_ilu_factorisation_property_and_solve(system):
     _check(dom, fd, A, exact, delta, odelta)
     m.iterative_Solve(fd, Sv_func="bicgstabl_GS", maxiter=4000, max_pass=10, s=4)
     assert it_ilu < fd.last_solve["iterations"], (it_ilu, fd.last_solve)
+
+
+def test_pl_ilu_four_variables(built_lib):
+    """Pl_ILU with 4 x 4 node blocks (thermo-elasticity: displacement + temperature): the factorisation property on the pattern and a
+    left-preconditioned solve whose TRUE residual (numpy, the oracle's matrix) meets the tolerance (the 1- and 3-variable block sizes run in the test above)."""
+    import ctypes as C
+    import metafem_b200 as m
+    dom, fd, A, exact = _make_system("thermo_elasticity")
+    try:
+        defect, levels = C.c_double(1.0), C.c_int32(0)
+        fd.ctx.call("mfb_ilu_selftest", C.byref(defect), C.byref(levels), None, 0)
+        assert defect.value < 1e-12 and 1 <= levels.value < 200, (defect.value, levels.value)
+        delta = m.iterative_Solve(fd, Sv_func="bicgstabl_GS", Pl_func="Pl_ILU", maxiter=4000, max_pass=10, s=4, want_delta=True)
+        it_ilu = fd.last_solve["iterations"]
+        assert fd.last_solve["converged"], fd.last_solve
+        gf = dom.globalfield
+        r = gf.residue - A @ delta
+        assert np.linalg.norm(r) / np.sqrt(len(r)) < gf.converge_tol * 1.01
+        m.iterative_Solve(fd, Sv_func="bicgstabl_GS", maxiter=4000, max_pass=10, s=4)
+        assert it_ilu <= fd.last_solve["iterations"], (it_ilu, fd.last_solve)
+    finally:
+        fd.close()
