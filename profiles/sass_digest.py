@@ -1,6 +1,7 @@
 """SASS digest of the hot kernels (runs without a GPU): mnemonic counts from `cuobjdump -sass` for
   * the NVRTC-compiled fused element kernel of the Neo-Hookean config (mfb_b0_nl) and of the thermo-elastic K_linear kernel,
-  * k_spmv_mr<3> (production SpMV), k_spmv_bsr<3> (round-1 SpMV), k_fused<0..24> in libmetafem_b200.so.
+  * k_spmv_mr<3> (production SpMV), k_spmv_bsr<3> (round-1 SpMV), k_fused<0..24>, k_dots, k_light, the Pl_ILU kernels
+    in libmetafem_b200.so.
 usage: python profiles/sass_digest.py > profiles/sass_digest_r2.txt"""
 import collections
 import os
@@ -60,8 +61,9 @@ def main():
         os.unlink(path)
     so = os.path.join(ROOT, "metafem.jl_b200", "libmetafem_b200.so")
     show("libmetafem_b200.so: SpMV", digest(so, r"k_spmv_mrILi3ELi5ELi16ELb0ELi4ELi0|k_spmv_bsrILi3ELi5ELi0ELi64"))
-    show("libmetafem_b200.so: fused vector programs", digest(so, r"k_fusedILi"))
-    show("libmetafem_b200.so: ILU sweeps (NV = 3)", digest(so, r"k_ilu_(sweep|factor)ILi3"))
+    show("libmetafem_b200.so: fused vector programs", digest(so, r"k_fusedILi|k_dotsILi|k_lightILi"))
+    show("libmetafem_b200.so: Pl_ILU (NV = 3): factorisation, production sweeps (stream kernel on FP32 factors), fallbacks",
+         digest(so, r"k_ilu_factorILi3|k_sweep_mrILi3ELi5ELi8ELi[12]ELi4EfLi3|k_ilu_sweep(_packed)?ILi3"))
 
 
 if __name__ == "__main__":
