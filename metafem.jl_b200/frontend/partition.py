@@ -25,10 +25,33 @@ class Subdomain:
         self.owned = owned            # uint8 [N_local]: 1 if this rank owns the node
 
 
+def _bisect(cen, idx, lo, n_parts, part):
+    """Recursive coordinate bisection: split the elements `idx` into n_parts boxes of (nearly) equal element count, cutting
+    the longest extent of the current box each time; ranks lo .. lo + n_parts - 1."""
+    if n_parts == 1:
+        part[idx] = lo
+        return
+    c = cen[:, idx]
+    axis = int(np.argmax(c.max(axis=1) - c.min(axis=1)))
+    left = n_parts // 2
+    order = idx[np.argsort(c[axis], kind="stable")]
+    cut = (len(idx) * left) // n_parts
+    _bisect(cen, order[:cut], lo, left, part)
+    _bisect(cen, order[cut:], lo + left, n_parts - left, part)
+
+
 def split_elements(tables, n_parts, method="slab"):
-    """Element -> rank. 'slab': contiguous blocks of the element list sorted by centroid x (then y, z)."""
+    """Element -> rank. 'slab': contiguous blocks of the element list sorted by centroid x (then y, z) -- what bench.py and the
+    GPU tests use (two neighbours per rank, every interface node shared by exactly two ranks). 'box': recursive coordinate
+    bisection into n_parts boxes (smaller interfaces, up to 26 neighbours, edge / corner nodes shared by 4 / 8 ranks; host logic
+    tested on CPU, tests/test_multi_gpu.py). 'contiguous': blocks of the element list as it is."""
     cp = tables.controlpoint_IDs
     n_el = cp.shape[1]
+    if method == "box":
+        cen = tables.x[:, cp - 1].mean(axis=1)
+        part = np.empty(n_el, np.int32)
+        _bisect(cen, np.arange(n_el), 0, n_parts, part)
+        return part
     if method == "contiguous":
         order = np.arange(n_el)
     else:

@@ -50,8 +50,11 @@ def test_partition_covers_mesh_and_interfaces_are_consistent():
     import metafem_b200  # noqa: F401
     from metafem_jl_b200.frontend import mesh as fmesh, partition as pt
     t = fmesh.box_tables((1.0, 1.0, 1.0), (5, 3, 2), "CUBE", groups=("left", "right"))
-    for P in (2, 3, 4):
-        part = pt.split_elements(t, P)
+    for P, method in ((2, "slab"), (3, "slab"), (4, "slab"), (4, "box"), (8, "box"), (5, "box")):
+        part = pt.split_elements(t, P, method=method)
+        assert np.array_equal(np.unique(part), np.arange(P))
+        counts = np.bincount(part, minlength=P)
+        assert counts.max() - counts.min() <= (1 if method == "slab" else P)               # balanced element counts
         subs = pt.make_subdomains(t, part)
         assert sum(s.tables.controlpoint_IDs.shape[1] for s in subs.values()) == t.controlpoint_IDs.shape[1]
         assert sum(int(s.owned.sum()) for s in subs.values()) == t.variable_size        # every node owned exactly once
@@ -66,7 +69,7 @@ def test_partition_covers_mesh_and_interfaces_are_consistent():
             assert sum(len(s.tables.bg_fIDs[g]) for s in subs.values()) == len(t.bg_fIDs[g])
 
 
-def _gloo_worker(rank, world, port, q):
+def _gloo_worker(rank, world, port, q, method="slab"):
     """Oracle on each rank's subdomain; interface exchange-add through gloo; compare with the undivided oracle."""
     import torch
     import torch.distributed as dist
@@ -98,7 +101,7 @@ def _gloo_worker(rank, world, port, q):
         oasm.assemble_Global_Variables(dom)
         osv.update_Time(dom); osv.initialize_dx(dom); oasm.K_linear_func(dom); osv.update_x_star(dom); oasm.K_nonlinear_func(dom)
 
-    part = pt.split_elements(t, world)
+    part = pt.split_elements(t, world, method=method)
     sub = pt.make_subdomains(t, part, ranks=[rank])[rank]
     dom = oracle_domain(sub.tables)
     fill(dom, t.x, lambda v: pt.scatter_field(sub, v))
@@ -147,6 +150,21 @@ def test_gloo_world2_subdomain_assembly_equals_global():
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(ok for _, ok in res), res
+
+
+def test_gloo_world4_box_partition_equals_global():
+    """The same check on a 2 x 2 box partition (recursive coordinate bisection): nodes on the centre line are shared by four
+    ranks, every rank has three neighbours."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 4, 29613, q, "box")) for r in range(4)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
     for p in procs:
         p.join(60)
     assert all(ok for _, ok in res), res
