@@ -145,6 +145,103 @@ class Pl_ILU:
         return b
 
 
+def _mix64(z):
+    """splitmix64 finaliser on uint64 arrays (the node hash of the library's elimination order)."""
+    z = (z + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+    z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)).astype(np.uint64)
+    z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)).astype(np.uint64)
+    return z ^ (z >> np.uint64(31))
+
+
+class Pl_ILU_block:
+    """Restatement of what the LIBRARY does for Pl_ILU (csrc/mfb_ilu.cu) -- not of cuSPARSE: the same zero-fill incomplete
+    factorisation, (L U)_ij = A_ij on the pattern, but on the nv x nv node blocks and in an elimination order chosen for
+    parallelism. Nodes get the priority hash mix64(id + 0x5bd1e995) of their 0-based id, are coloured greedily in descending
+    priority (colour = smallest one no higher-priority neighbour carries) and eliminated colour class by colour class, ties by
+    the hash; unit lower factor L_ik = A_ik U_kk^-1, no pivoting. `levels` is the dependency depth of that order (what the
+    library reports). Vectors are variable-major ([nv][N]) like GlobalField.x. Plain loops: small systems only."""
+
+    def __init__(self, A, nv, order="color"):
+        import scipy.sparse as sps
+        n = A.shape[0]
+        A = sps.csr_matrix((A.data.copy(), A.col - 1, A.ptr - 1), shape=(n, n)) if hasattr(A, "ptr") else sps.csr_matrix(A)
+        N = n // nv
+        self.nv, self.N = nv, N
+        # node graph and blocks: block (i, j)[v][w] = A[v N + i, w N + j]
+        coo = A.tocoo()
+        blocks = {}
+        for r, c, val in zip(coo.row, coo.col, coo.data):
+            i, v, j, w = r % N, r // N, c % N, c // N
+            blocks.setdefault((i, j), np.zeros((nv, nv)))[v, w] = val
+        nbr = [[] for _ in range(N)]
+        for (i, j) in blocks:
+            if i != j:
+                nbr[i].append(j)
+        with np.errstate(over="ignore"):
+            key = _mix64(np.arange(N, dtype=np.uint64) + np.uint64(0x5bd1e995))
+        if order == "color":
+            color = np.full(N, -1)
+            for i in np.argsort(key, kind="stable")[::-1]:           # descending priority
+                used = {color[j] for j in nbr[i] if color[j] >= 0}
+                c = 0
+                while c in used:
+                    c += 1
+                color[i] = c
+            key = (color.astype(np.uint64) << np.uint64(56)) | (key >> np.uint64(8))
+            self.n_colors = int(color.max()) + 1
+        seq = np.argsort(key, kind="stable")                          # elimination order
+        pos = np.empty(N, np.int64)
+        pos[seq] = np.arange(N)
+        self.pos, self.seq = pos, seq
+        F = {k: b.copy() for k, b in blocks.items()}
+        dinv = [None] * N
+        level = np.zeros(N, np.int64)
+        for i in seq:
+            low = sorted((j for j in nbr[i] if pos[j] < pos[i]), key=lambda j: pos[j])
+            for k in low:
+                L = F[(i, k)] @ dinv[k]
+                F[(i, k)] = L
+                for j in nbr[k] + [k]:
+                    if j != k and pos[j] > pos[k] and (i, j) in F:
+                        F[(i, j)] = F[(i, j)] - L @ F[(k, j)]
+                level[i] = max(level[i], level[k] + 1)
+            dinv[i] = np.linalg.inv(F[(i, i)])
+        self.F, self.dinv, self.nbr, self.blocks = F, dinv, nbr, blocks
+        self.levels = int(level.max()) + 1
+
+    def product_defect(self):
+        """max |(L U - A)_ij| over the block pattern / max |A_ij|."""
+        pos, F, worst, amax = self.pos, self.F, 0.0, 0.0
+        I = np.eye(self.nv)
+        for (i, j), a in self.blocks.items():
+            s = np.zeros_like(a)
+            for k in set(self.nbr[i] + [i]) & set(self.nbr[j] + [j]):
+                if pos[k] > min(pos[i], pos[j]):
+                    continue
+                Lik = I if k == i else (F[(i, k)] if pos[k] < pos[i] else None)
+                Ukj = F.get((k, j)) if pos[j] >= pos[k] else None
+                if Lik is not None and Ukj is not None:
+                    s = s + Lik @ Ukj
+            worst, amax = max(worst, np.abs(s - a).max()), max(amax, np.abs(a).max())
+        return worst / amax
+
+    def __call__(self, b):
+        nv, N, pos, F = self.nv, self.N, self.pos, self.F
+        v = np.asarray(b, dtype=float).reshape(nv, N).T.copy()        # [N][nv]
+        for i in self.seq:                                            # forward, unit L
+            for k in self.nbr[i]:
+                if pos[k] < pos[i]:
+                    v[i] -= F[(i, k)] @ v[k]
+        for i in self.seq[::-1]:                                      # backward
+            acc = v[i].copy()
+            for j in self.nbr[i]:
+                if pos[j] > pos[i]:
+                    acc -= F[(i, j)] @ v[j]
+            v[i] = self.dinv[i] @ acc
+        b[:] = v.T.ravel()
+        return b
+
+
 def Identity(b):
     return b
 

@@ -64,3 +64,24 @@ def test_oracle_pl_ilu(system):
     assert np.linalg.norm(r) / np.sqrt(len(r)) < gf.converge_tol * 1.01, dom.last_solve
     osv.iterative_Solve(dom, osv.bicgstabl_GS, max_pass=10, maxiter=4000, s=4)
     assert it_ilu < sum(dom.last_solve["iters"])
+
+
+@pytest.mark.parametrize("order", ["color", "hash"])
+def test_oracle_block_ilu_in_the_library_order(system, order):
+    """The restatement of the LIBRARY's Pl_ILU (block ILU(0), elimination by colour classes of a greedy colouring in hash
+    priority): (L U)_ij = A_ij on the block pattern, the dependency depth is bounded by the number of colours, and the
+    left-preconditioned solve reaches the tolerance in no more iterations than the reference-order scalar ILU needs plus a
+    margin (the order is chosen for parallelism; it must not cost convergence)."""
+    dom, A, exact = system
+    gf = dom.globalfield
+    nv = len(dom.spec["basic_vars"])
+    P = osv.Pl_ILU_block(A, nv, order=order)
+    assert P.product_defect() < 1e-12
+    if order == "color":
+        assert P.levels <= P.n_colors
+    delta = osv.iterative_Solve(dom, osv.bicgstabl_GS, max_pass=10, maxiter=4000, s=4, Pl_func=lambda M: osv.Pl_ILU_block(M, nv, order=order))
+    it_block = sum(dom.last_solve["iters"])
+    r = gf.residue - A @ delta
+    assert np.linalg.norm(r) / np.sqrt(len(r)) < gf.converge_tol * 1.01, dom.last_solve
+    osv.iterative_Solve(dom, osv.bicgstabl_GS, max_pass=10, maxiter=4000, s=4)
+    assert it_block <= sum(dom.last_solve["iters"]), (it_block, dom.last_solve)
