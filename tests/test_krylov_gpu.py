@@ -122,8 +122,13 @@ def test_pl_ilu_four_variables(built_lib):
     dom, fd, A, exact = _make_system("thermo_elasticity")
     try:
         defect, levels = C.c_double(1.0), C.c_int32(0)
-        fd.ctx.call("mfb_ilu_selftest", C.byref(defect), C.byref(levels), None, 0)
-        assert defect.value < 1e-12 and 1 <= levels.value < 200, (defect.value, levels.value)
+        P = osv.Pl_ILU_block(A, 4)
+        v = np.random.default_rng(12).standard_normal(A.shape[0])
+        want = P(v.copy())
+        got = np.ascontiguousarray(v.copy())
+        fd.ctx.call("mfb_ilu_selftest", C.byref(defect), C.byref(levels), m.lib.ptr(got), len(got))
+        assert defect.value < 1e-12 and levels.value == P.levels, (defect.value, levels.value, P.levels)
+        assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max(), np.abs(got - want).max() / np.abs(want).max()
         delta = m.iterative_Solve(fd, Sv_func="bicgstabl_GS", Pl_func="Pl_ILU", maxiter=4000, max_pass=10, s=4, want_delta=True)
         it_ilu = fd.last_solve["iterations"]
         assert fd.last_solve["converged"], fd.last_solve
