@@ -632,7 +632,7 @@ __device__ __forceinline__ double block_sum256(double v, double* sh) {
 
 // Tail of every reducing kernel (256 threads per block; thread 0 of each block has already stored the block's partial sums at
 // partials[d * gridDim.x + blockIdx.x]). The last block to arrive folds, exchanges with the other ranks, applies the scalar ops.
-__device__ __noinline__ void reduce_tail(const RedCtx& R, int nd, const ScOp& o0, const ScOp& o1) {
+__device__ __noinline__ void reduce_tail(const RedCtx& R, int nd, const ScOp& o0, const ScOp& o1, int n_partials = 0) {
     __shared__ int s_last;
     __shared__ double s_w[8];
     __shared__ double s_loc[P2P_MAXV];
@@ -645,7 +645,7 @@ __device__ __noinline__ void reduce_tail(const RedCtx& R, int nd, const ScOp& o0
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    const int nb = gridDim.x;
+    const int nb = n_partials > 0 ? n_partials : (int)gridDim.x;    // kernels that run VIRTUAL blocks store one partial per virtual block
     for (int d = 0; d < nd; ++d) {
         double v = 0.0;
         for (int b = tid; b < nb; b += 256) v += __ldcg(R.partials + (size_t)d * nb + b);
@@ -839,7 +839,7 @@ __global__ void __launch_bounds__(256) k_fused(const Fused* __restrict__ Fg, con
 // every thread takes J pairs per step and issues all 2 J ND loads before the first multiply.
 template <int ND, int J>
 __global__ void __launch_bounds__(256, 3) k_dots(const Fused* __restrict__ Fg, const RedCtx R, int64_t n, const unsigned char* owned,
-                                                 int nv) {
+                                                 int nv, int vblocks) {
     if (stopped(R)) return;
     __shared__ const double* s_x[ND];
     __shared__ const double* s_y[ND];
@@ -855,13 +855,17 @@ __global__ void __launch_bounds__(256, 3) k_dots(const Fused* __restrict__ Fg, c
     const double* yp[ND];
 #pragma unroll
     for (int d = 0; d < ND; ++d) { xp[d] = d < nd ? s_x[d] : nullptr; yp[d] = d < nd ? s_y[d] : nullptr; }
+    // The grid is ONE wave of CTAs; each CTA runs the VIRTUAL blocks vb = blockIdx.x, blockIdx.x + gridDim.x, ... of a vblocks-wide
+    // grid: which elements a thread sums, in which order, and which partial they land in depend on vblocks only, so the result
+    // is bit-identical for every physical grid size (the iteration count of BiCGStab hangs on these roundings)
+    const int64_t np = (n + 1) >> 1;
+    const int64_t stride = (int64_t)vblocks * 256;
+    const double2 zero2 = make_double2(0.0, 0.0);
+    for (int vb = blockIdx.x; vb < vblocks; vb += gridDim.x) {
     double acc[ND];
 #pragma unroll
     for (int d = 0; d < ND; ++d) acc[d] = 0.0;
-    const int64_t np = (n + 1) >> 1;
-    const int64_t stride = (int64_t)gridDim.x * 256;
-    const double2 zero2 = make_double2(0.0, 0.0);
-    for (int64_t p0 = blockIdx.x * (int64_t)256 + tid; p0 < np; p0 += J * stride) {
+    for (int64_t p0 = vb * (int64_t)256 + tid; p0 < np; p0 += J * stride) {
         double2 xv[J][ND], yv[J][ND];
 #pragma unroll
         for (int j = 0; j < J; ++j) {
@@ -891,9 +895,10 @@ __global__ void __launch_bounds__(256, 3) k_dots(const Fused* __restrict__ Fg, c
     for (int d = 0; d < ND; ++d)
         if (d < nd) {
             const double w = block_sum256(acc[d], s_w);
-            if (tid == 0) R.partials[(size_t)d * gridDim.x + blockIdx.x] = w;
+            if (tid == 0) R.partials[(size_t)d * vblocks + vb] = w;
         }
-    reduce_tail(R, nd, s_ops[0], s_ops[1]);
+    }
+    reduce_tail(R, nd, s_ops[0], s_ops[1], vblocks);
 }
 
 // Light programs: at most two single-term updates y_u = ay y_u + c x_u followed by at most four dots (the first BiCG updates,
@@ -902,7 +907,7 @@ __global__ void __launch_bounds__(256, 3) k_dots(const Fused* __restrict__ Fg, c
 // targets are distinct and are read neither by a later update nor -- through a pointer -- by a dot.
 template <int NU, int ND, int J>
 __global__ void __launch_bounds__(256, 3) k_light(const Fused* __restrict__ Fg, const RedCtx R, int64_t n, const unsigned char* owned,
-                                                  int nv) {
+                                                  int nv, int vblocks) {
     if (stopped(R)) return;
     __shared__ double* s_y[NU];
     __shared__ const double* s_x[NU];
@@ -936,13 +941,16 @@ __global__ void __launch_bounds__(256, 3) k_light(const Fused* __restrict__ Fg, 
     }
     const double* dxp[ND > 0 ? ND : 1];
     const double* dyp[ND > 0 ? ND : 1];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { dxp[d] = d < nd ? s_dx[d] : nullptr; dyp[d] = d < nd ? s_dy[d] : nullptr; }
+    const int64_t np = (n + 1) >> 1;
+    const int64_t stride = (int64_t)vblocks * 256;                    // virtual blocks, as in k_dots
+    const double2 zero2 = make_double2(0.0, 0.0);
+    for (int vb = blockIdx.x; vb < vblocks; vb += gridDim.x) {
     double acc[ND > 0 ? ND : 1];
 #pragma unroll
-    for (int d = 0; d < ND; ++d) { dxp[d] = d < nd ? s_dx[d] : nullptr; dyp[d] = d < nd ? s_dy[d] : nullptr; acc[d] = 0.0; }
-    const int64_t np = (n + 1) >> 1;
-    const int64_t stride = (int64_t)gridDim.x * 256;
-    const double2 zero2 = make_double2(0.0, 0.0);
-    for (int64_t p0 = blockIdx.x * (int64_t)256 + tid; p0 < np; p0 += J * stride) {
+    for (int d = 0; d < ND; ++d) acc[d] = 0.0;
+    for (int64_t p0 = vb * (int64_t)256 + tid; p0 < np; p0 += J * stride) {
         double2 yv[J][NU], xv[J][NU], dxv[J][ND > 0 ? ND : 1], dyv[J][ND > 0 ? ND : 1];
 #pragma unroll
         for (int j = 0; j < J; ++j) {
@@ -991,10 +999,11 @@ __global__ void __launch_bounds__(256, 3) k_light(const Fused* __restrict__ Fg, 
         for (int d = 0; d < ND; ++d)
             if (d < nd) {
                 const double w = block_sum256(acc[d], s_w);
-                if (tid == 0) R.partials[(size_t)d * gridDim.x + blockIdx.x] = w;
+                if (tid == 0) R.partials[(size_t)d * vblocks + vb] = w;
             }
-        reduce_tail(R, nd, s_ops[0], s_ops[1]);
     }
+    }
+    if constexpr (ND > 0) reduce_tail(R, nd, s_ops[0], s_ops[1], vblocks);
 }
 
 // ---- SpMV, multi-row streams: one warp walks the CONCATENATED value stream of RW consecutive block rows (they are contiguous
@@ -1838,10 +1847,13 @@ struct Solver {
         const Fused* dev = reinterpret_cast<const Fused*>(ctx->kprog.p) + idx;
         const int nd = F.n_dot;
         const bool light = light_ok(F);
+        // k_dots / k_light hold 3 CTAs per SM (launch bounds): ONE wave of 3 x 148 CTAs runs the RED_BLOCKS virtual blocks, so that
+        // the per-CTA prologue is paid once and no partial wave trails (RED_BLOCKS = 8 x 148 CTAs would be 2.67 waves)
+        constexpr int WAVE3 = 3 * 148;
         if (nd == 0) {
             const RedCtx R0 = stopctx();
-            if (light && F.n_upd == 1) LAUNCH((k_light<1, 0, 4>), RED_BLOCKS, TPB, dev, R0, n, (const unsigned char*)nullptr, ctx->n_var);
-            else if (light) LAUNCH((k_light<2, 0, 2>), RED_BLOCKS, TPB, dev, R0, n, (const unsigned char*)nullptr, ctx->n_var);
+            if (light && F.n_upd == 1) LAUNCH((k_light<1, 0, 4>), WAVE3, TPB, dev, R0, n, (const unsigned char*)nullptr, ctx->n_var, RED_BLOCKS);
+            else if (light) LAUNCH((k_light<2, 0, 2>), WAVE3, TPB, dev, R0, n, (const unsigned char*)nullptr, ctx->n_var, RED_BLOCKS);
             else LAUNCH((k_fused<0>), RED_BLOCKS, TPB, dev, R0, n, (const unsigned char*)nullptr, ctx->n_var);
             return MFB_OK;
         }
@@ -1849,18 +1861,18 @@ struct Solver {
         const RedCtx R = redctx();
         if (light) {
             if (F.n_upd == 1) {
-                if (nd == 1) LAUNCH((k_light<1, 1, 2>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
-                else if (nd == 2) LAUNCH((k_light<1, 2, 2>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
-                else LAUNCH((k_light<1, 4, 1>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
+                if (nd == 1) LAUNCH((k_light<1, 1, 2>), WAVE3, TPB, dev, R, n, mask(), ctx->n_var, RED_BLOCKS);
+                else if (nd == 2) LAUNCH((k_light<1, 2, 2>), WAVE3, TPB, dev, R, n, mask(), ctx->n_var, RED_BLOCKS);
+                else LAUNCH((k_light<1, 4, 1>), WAVE3, TPB, dev, R, n, mask(), ctx->n_var, RED_BLOCKS);
             } else {
-                if (nd <= 2) LAUNCH((k_light<2, 2, 1>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
-                else LAUNCH((k_light<2, 4, 1>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
+                if (nd <= 2) LAUNCH((k_light<2, 2, 1>), WAVE3, TPB, dev, R, n, mask(), ctx->n_var, RED_BLOCKS);
+                else LAUNCH((k_light<2, 4, 1>), WAVE3, TPB, dev, R, n, mask(), ctx->n_var, RED_BLOCKS);
             }
             return after_reduce(R, nd, F.ops[0], F.ops[1]);
         }
         if (F.n_upd == 0 && nd <= 2) {                     // one or two plain dots: more loads in flight per thread
-            if (nd == 1) LAUNCH((k_dots<1, 4>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
-            else LAUNCH((k_dots<2, 2>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
+            if (nd == 1) LAUNCH((k_dots<1, 4>), WAVE3, TPB, dev, R, n, mask(), ctx->n_var, RED_BLOCKS);
+            else LAUNCH((k_dots<2, 2>), WAVE3, TPB, dev, R, n, mask(), ctx->n_var, RED_BLOCKS);
             return after_reduce(R, nd, F.ops[0], F.ops[1]);
         }
         if (nd <= 2) LAUNCH((k_fused<2>), RED_BLOCKS, TPB, dev, R, n, mask(), ctx->n_var);
