@@ -862,41 +862,41 @@ __global__ void __launch_bounds__(256, 3) k_dots(const Fused* __restrict__ Fg, c
     const int64_t stride = (int64_t)vblocks * 256;
     const double2 zero2 = make_double2(0.0, 0.0);
     for (int vb = blockIdx.x; vb < vblocks; vb += gridDim.x) {
-    double acc[ND];
+        double acc[ND];
 #pragma unroll
-    for (int d = 0; d < ND; ++d) acc[d] = 0.0;
-    for (int64_t p0 = vb * (int64_t)256 + tid; p0 < np; p0 += J * stride) {
-        double2 xv[J][ND], yv[J][ND];
+        for (int d = 0; d < ND; ++d) acc[d] = 0.0;
+        for (int64_t p0 = vb * (int64_t)256 + tid; p0 < np; p0 += J * stride) {
+            double2 xv[J][ND], yv[J][ND];
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-            const int64_t pj = p0 + j * stride;
-            const bool in = pj < np;
+            for (int j = 0; j < J; ++j) {
+                const int64_t pj = p0 + j * stride;
+                const bool in = pj < np;
 #pragma unroll
-            for (int d = 0; d < ND; ++d) {
-                xv[j][d] = (in && xp[d]) ? ld2(xp[d], pj, n) : zero2;
-                yv[j][d] = (in && yp[d]) ? (yp[d] == xp[d] ? xv[j][d] : ld2(yp[d], pj, n)) : zero2;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            const int64_t pj = p0 + j * stride;
-            if (pj < np) {
-                double2 w0 = make_double2(1.0, 2 * pj + 1 < n ? 1.0 : 0.0);
-                if (owned != nullptr) {                     // count every node once (on its owner)
-                    w0.x = owned[(2 * pj) / nv] ? 1.0 : 0.0;
-                    if (w0.y != 0.0) w0.y = owned[(2 * pj + 1) / nv] ? 1.0 : 0.0;
+                for (int d = 0; d < ND; ++d) {
+                    xv[j][d] = (in && xp[d]) ? ld2(xp[d], pj, n) : zero2;
+                    yv[j][d] = (in && yp[d]) ? (yp[d] == xp[d] ? xv[j][d] : ld2(yp[d], pj, n)) : zero2;
                 }
+            }
 #pragma unroll
-                for (int d = 0; d < ND; ++d) acc[d] += w0.x * (xv[j][d].x * yv[j][d].x) + w0.y * (xv[j][d].y * yv[j][d].y);
+            for (int j = 0; j < J; ++j) {
+                const int64_t pj = p0 + j * stride;
+                if (pj < np) {
+                    double2 w0 = make_double2(1.0, 2 * pj + 1 < n ? 1.0 : 0.0);
+                    if (owned != nullptr) {                     // count every node once (on its owner)
+                        w0.x = owned[(2 * pj) / nv] ? 1.0 : 0.0;
+                        if (w0.y != 0.0) w0.y = owned[(2 * pj + 1) / nv] ? 1.0 : 0.0;
+                    }
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) acc[d] += w0.x * (xv[j][d].x * yv[j][d].x) + w0.y * (xv[j][d].y * yv[j][d].y);
+                }
             }
         }
-    }
 #pragma unroll
-    for (int d = 0; d < ND; ++d)
-        if (d < nd) {
-            const double w = block_sum256(acc[d], s_w);
-            if (tid == 0) R.partials[(size_t)d * vblocks + vb] = w;
-        }
+        for (int d = 0; d < ND; ++d)
+            if (d < nd) {
+                const double w = block_sum256(acc[d], s_w);
+                if (tid == 0) R.partials[(size_t)d * vblocks + vb] = w;
+            }
     }
     reduce_tail(R, nd, s_ops[0], s_ops[1], vblocks);
 }
@@ -947,61 +947,61 @@ __global__ void __launch_bounds__(256, 3) k_light(const Fused* __restrict__ Fg, 
     const int64_t stride = (int64_t)vblocks * 256;                    // virtual blocks, as in k_dots
     const double2 zero2 = make_double2(0.0, 0.0);
     for (int vb = blockIdx.x; vb < vblocks; vb += gridDim.x) {
-    double acc[ND > 0 ? ND : 1];
+        double acc[ND > 0 ? ND : 1];
 #pragma unroll
-    for (int d = 0; d < ND; ++d) acc[d] = 0.0;
-    for (int64_t p0 = vb * (int64_t)256 + tid; p0 < np; p0 += J * stride) {
-        double2 yv[J][NU], xv[J][NU], dxv[J][ND > 0 ? ND : 1], dyv[J][ND > 0 ? ND : 1];
+        for (int d = 0; d < ND; ++d) acc[d] = 0.0;
+        for (int64_t p0 = vb * (int64_t)256 + tid; p0 < np; p0 += J * stride) {
+            double2 yv[J][NU], xv[J][NU], dxv[J][ND > 0 ? ND : 1], dyv[J][ND > 0 ? ND : 1];
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-            const int64_t pj = p0 + j * stride;
-            const bool in = pj < np;
+            for (int j = 0; j < J; ++j) {
+                const int64_t pj = p0 + j * stride;
+                const bool in = pj < np;
 #pragma unroll
-            for (int u = 0; u < NU; ++u) {
-                yv[j][u] = (in && yp[u] && ay[u] != 0.0) ? ld2(yp[u], pj, n) : zero2;
-                xv[j][u] = (in && xp[u]) ? ld2(xp[u], pj, n) : zero2;
-            }
-#pragma unroll
-            for (int d = 0; d < ND; ++d) {
-                dxv[j][d] = (in && dxp[d]) ? ld2(dxp[d], pj, n) : zero2;
-                dyv[j][d] = (in && dyp[d] && dyp[d] != dxp[d]) ? ld2(dyp[d], pj, n) : zero2;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            const int64_t pj = p0 + j * stride;
-            if (pj >= np) continue;
-            double2 r0 = zero2;                               // result of the last update (dot operand)
-#pragma unroll
-            for (int u = 0; u < NU; ++u)
-                if (u < nu) {
-                    r0 = make_double2(ay[u] * yv[j][u].x + c[u] * xv[j][u].x, ay[u] * yv[j][u].y + c[u] * xv[j][u].y);
-                    st2(yp[u], pj, n, r0);
-                }
-            if constexpr (ND > 0) {
-                double2 w0 = make_double2(1.0, 2 * pj + 1 < n ? 1.0 : 0.0);
-                if (owned != nullptr) {                       // count every node once (on its owner)
-                    w0.x = owned[(2 * pj) / nv] ? 1.0 : 0.0;
-                    if (w0.y != 0.0) w0.y = owned[(2 * pj + 1) / nv] ? 1.0 : 0.0;
+                for (int u = 0; u < NU; ++u) {
+                    yv[j][u] = (in && yp[u] && ay[u] != 0.0) ? ld2(yp[u], pj, n) : zero2;
+                    xv[j][u] = (in && xp[u]) ? ld2(xp[u], pj, n) : zero2;
                 }
 #pragma unroll
-                for (int d = 0; d < ND; ++d)
-                    if (d < nd) {
-                        const double2 X = dxp[d] ? dxv[j][d] : r0;
-                        const double2 Y = dyp[d] ? (dyp[d] == dxp[d] ? X : dyv[j][d]) : r0;
-                        acc[d] += w0.x * (X.x * Y.x) + w0.y * (X.y * Y.y);
+                for (int d = 0; d < ND; ++d) {
+                    dxv[j][d] = (in && dxp[d]) ? ld2(dxp[d], pj, n) : zero2;
+                    dyv[j][d] = (in && dyp[d] && dyp[d] != dxp[d]) ? ld2(dyp[d], pj, n) : zero2;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int64_t pj = p0 + j * stride;
+                if (pj >= np) continue;
+                double2 r0 = zero2;                               // result of the last update (dot operand)
+#pragma unroll
+                for (int u = 0; u < NU; ++u)
+                    if (u < nu) {
+                        r0 = make_double2(ay[u] * yv[j][u].x + c[u] * xv[j][u].x, ay[u] * yv[j][u].y + c[u] * xv[j][u].y);
+                        st2(yp[u], pj, n, r0);
                     }
+                if constexpr (ND > 0) {
+                    double2 w0 = make_double2(1.0, 2 * pj + 1 < n ? 1.0 : 0.0);
+                    if (owned != nullptr) {                       // count every node once (on its owner)
+                        w0.x = owned[(2 * pj) / nv] ? 1.0 : 0.0;
+                        if (w0.y != 0.0) w0.y = owned[(2 * pj + 1) / nv] ? 1.0 : 0.0;
+                    }
+#pragma unroll
+                    for (int d = 0; d < ND; ++d)
+                        if (d < nd) {
+                            const double2 X = dxp[d] ? dxv[j][d] : r0;
+                            const double2 Y = dyp[d] ? (dyp[d] == dxp[d] ? X : dyv[j][d]) : r0;
+                            acc[d] += w0.x * (X.x * Y.x) + w0.y * (X.y * Y.y);
+                        }
+                }
             }
         }
-    }
-    if constexpr (ND > 0) {
+        if constexpr (ND > 0) {
 #pragma unroll
-        for (int d = 0; d < ND; ++d)
-            if (d < nd) {
-                const double w = block_sum256(acc[d], s_w);
-                if (tid == 0) R.partials[(size_t)d * vblocks + vb] = w;
-            }
-    }
+            for (int d = 0; d < ND; ++d)
+                if (d < nd) {
+                    const double w = block_sum256(acc[d], s_w);
+                    if (tid == 0) R.partials[(size_t)d * vblocks + vb] = w;
+                }
+        }
     }
     if constexpr (ND > 0) reduce_tail(R, nd, s_ops[0], s_ops[1], vblocks);
 }
